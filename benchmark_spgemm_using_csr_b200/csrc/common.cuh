@@ -1,0 +1,306 @@
+// common.cuh -- shared definitions of the B200 SpGEMM pipeline (sm_100a).
+//
+// Pipeline (replaces bhsparse::spgemm_cuda, SpGEMM_cuda/bhsparse.h:297-339):
+//   1. k_row_products     per-row intermediate-product upper bound + symbolic bins
+//   2. k_bin_scatter      rows -> per-bin queues (device prefix sums, no host pass)
+//   3. symbolic kernels   exact nnz(C_i) per row, one kernel family per bin
+//   4. scan kernels       nnz(C_i) -> rowptrC (int32 + int64), numeric bins
+//   5. numeric kernels    C rows written sorted, directly at rowptrC[i]
+// The reference's over-allocated Ct + compaction (create_Ct / copyCt2C,
+// bhsparse_cuda.h:285-301, 2813-2911) and its host re-allocation loop
+// (:2527-2780) do not exist here: step 3 sizes C exactly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bhb {
+
+constexpr int EMPTY_KEY = -1;
+constexpr int SORT_PAD = 0x7fffffff;
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- bins ------------------------------------------------------------------
+// Symbolic bins are chosen by p = upper bound of the row (products); numeric
+// bins by c = exact nnz(C_i) (and p for the tiny rows).  They play the role of
+// the reference's 128 segments (bhsparse.h:373-407) but the boundaries follow
+// the B200's 227 KB shared memory instead of 32/64/128/256/512/2304.
+enum SymBin {
+    SB_ZERO = 0,   // p == 0            -> nnz(C_i) = 0, no kernel   (ESC_0, bhsparse_cuda.h:1582)
+    SB_ONE = 1,    // p == 1            -> nnz(C_i) = 1, no kernel   (ESC_1, :1597)
+    SB_ESC = 2,    // 2 <= p <= 32      -> warp-shuffle ESC          (ESC_2heap, :653)
+    SB_G128 = 3,   // p <= 96           -> group hash, T = 128       (ESC_bitonic, :1400)
+    SB_G256 = 4,   // p <= 192
+    SB_G512 = 5,   // p <= 384
+    SB_G1024 = 6,  // p <= 768
+    SB_G2048 = 7,  // p <= 1536
+    SB_G4096 = 8,  // p <= 3072
+    SB_B8192 = 9,  // p <= 6144         -> block hash                (EM_mergepath, :1902)
+    SB_B16384 = 10, // p <= 12288
+    SB_B32768 = 11, // p <= 24576
+    SB_LARGE = 12,  // beyond           -> global bitmap             (EM_mergepath_global, :2270)
+    SB_COUNT = 13
+};
+enum NumBin {
+    NB_ZERO = 0,   // c == 0
+    NB_ONE = 1,    // p == 1
+    NB_ESC = 2,    // 2 <= p <= 32
+    NB_G64 = 3,    // c <= 32   T = 64
+    NB_G128 = 4,   // c <= 64
+    NB_G256 = 5,   // c <= 128
+    NB_G512 = 6,   // c <= 256
+    NB_G1024 = 7,  // c <= 512
+    NB_G2048 = 8,  // c <= 1024
+    NB_B4096 = 9,  // c <= 2048  block hash
+    NB_B8192 = 10, // c <= 4096
+    NB_B16384 = 11, // c <= 8192
+    NB_LARGE = 12,  // beyond    global bitmap-rank accumulation
+    NB_COUNT = 13
+};
+constexpr int MAX_BINS = 16;
+
+__host__ __device__ __forceinline__ int sym_bin_of(int p)
+{
+    if (p <= 1) return p;
+    if (p <= 32) return SB_ESC;
+    if (p <= 96) return SB_G128;
+    if (p <= 192) return SB_G256;
+    if (p <= 384) return SB_G512;
+    if (p <= 768) return SB_G1024;
+    if (p <= 1536) return SB_G2048;
+    if (p <= 3072) return SB_G4096;
+    if (p <= 6144) return SB_B8192;
+    if (p <= 12288) return SB_B16384;
+    if (p <= 24576) return SB_B32768;
+    return SB_LARGE;
+}
+__host__ __device__ __forceinline__ int num_bin_of(int p, int c)
+{
+    if (p <= 1) return p;
+    if (p <= 32) return NB_ESC;
+    if (c <= 32) return NB_G64;
+    if (c <= 64) return NB_G128;
+    if (c <= 128) return NB_G256;
+    if (c <= 256) return NB_G512;
+    if (c <= 512) return NB_G1024;
+    if (c <= 1024) return NB_G2048;
+    if (c <= 2048) return NB_B4096;
+    if (c <= 4096) return NB_B8192;
+    if (c <= 8192) return NB_B16384;
+    return NB_LARGE;
+}
+
+// Device-side counters of one spgemm call (one small struct, zeroed per call,
+// copied back once after stage 1 and once after the scan).
+struct Counters {
+    unsigned long long products;   // sum of per-row products (_nnzCt_full, bhsparse.h:368)
+    unsigned long long nnzC;       // set by the scan
+    int max_row_products;
+    int row_overflow;              // a row's product count did not fit int32
+    int sym_bin[MAX_BINS];
+    int num_bin[MAX_BINS];
+    int sym_cursor[MAX_BINS];
+    int num_cursor[MAX_BINS];
+};
+struct BinOffsets {
+    int off[MAX_BINS + 1];
+};
+
+// ---- hashing ---------------------------------------------------------------
+template <int LOG2T>
+__device__ __forceinline__ int hash_slot(int c)
+{
+    return (int)(((unsigned)c * 2654435761u) >> (32 - LOG2T));
+}
+
+// Insert column c into an open-addressing table (linear probing).  Returns the
+// slot; is_new is true for the thread whose CAS claimed an empty slot.
+template <int LOG2T>
+__device__ __forceinline__ int table_insert(int *keys, int c, bool &is_new)
+{
+    constexpr int MASK = (1 << LOG2T) - 1;
+    volatile int *vk = keys;
+    int h = hash_slot<LOG2T>(c);
+    is_new = false;
+    while (true) {
+        int k = vk[h];
+        if (k == c) return h;
+        if (k == EMPTY_KEY) {
+            int old = atomicCAS(&keys[h], EMPTY_KEY, c);
+            if (old == EMPTY_KEY) {
+                is_new = true;
+                return h;
+            }
+            if (old == c) return h;
+        }
+        h = (h + 1) & MASK;
+    }
+}
+template <int LOG2T>
+__device__ __forceinline__ int table_find(const int *keys, int c)
+{
+    constexpr int MASK = (1 << LOG2T) - 1;
+    int h = hash_slot<LOG2T>(c);
+    while (keys[h] != c) h = (h + 1) & MASK;
+    return h;
+}
+
+// ---- sub-warp groups ---------------------------------------------------------
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane)
+{
+    if (G == 32) return FULL;
+    return ((1u << (G & 31)) - 1u) << (lane & ~(G - 1));
+}
+
+// Bitonic sort of N = G*R keys held R per lane in blocked order (element index
+// i = gl*R + r), ascending.  Strides below R are register compare-exchanges,
+// strides of R and above are one __shfl_xor + one min/max per key.
+template <int G, int R>
+__device__ __forceinline__ void bitonic_sort_regs(int (&x)[R], const int gl, const unsigned gmask)
+{
+    constexpr int N = G * R;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= R) {
+                const int d = j / R;
+                const bool lower = (gl & d) == 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = gl * R + r;
+                    const bool asc = (k == N) ? true : ((i & k) == 0);
+                    const int y = __shfl_xor_sync(gmask, x[r], d, G);
+                    x[r] = (lower == asc) ? min(x[r], y) : max(x[r], y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & j) == 0) {
+                        const int i = gl * R + r;
+                        const bool asc = (k == N) ? true : ((i & k) == 0);
+                        const int lo = min(x[r], x[r + j]);
+                        const int hi = max(x[r], x[r + j]);
+                        x[r] = asc ? lo : hi;
+                        x[r + j] = asc ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Bitonic sort of sk[0..N) (N a power of two) in shared memory by one group.
+template <int G>
+__device__ __forceinline__ void bitonic_sort_smem_group(int *sk, const int N, const int gl, const unsigned gmask)
+{
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = gl; t < (N >> 1); t += G) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const int a = sk[i], b = sk[p];
+                const bool asc = (i & k) == 0;
+                if ((a > b) == asc) {
+                    sk[i] = b;
+                    sk[p] = a;
+                }
+            }
+            __syncwarp(gmask);
+        }
+    }
+}
+// Same by a whole block.
+__device__ __forceinline__ void bitonic_sort_smem_block(int *sk, const int N)
+{
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const int a = sk[i], b = sk[p];
+                const bool asc = (i & k) == 0;
+                if ((a > b) == asc) {
+                    sk[i] = b;
+                    sk[p] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int v)
+{
+    return v <= 2 ? 2 : 1 << (32 - __clz(v - 1));
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// Block-wide sum; every thread gets the result.  `red` holds >= 33 elements.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        T w = (lane < (int)((blockDim.x + 31) >> 5)) ? red[lane] : T(0);
+        w = warp_sum(w);
+        if (lane == 0) red[32] = w;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// ---- launch interface (defined in the stage_*.cu files, called by context.cu) -
+struct Csr {
+    const int *rowptr;
+    const int *col;
+    const void *val;
+};
+struct LaunchCtx {
+    cudaStream_t stream;
+    int sm_count;
+    int *launches;   // incremented per kernel launch
+};
+
+// stage_count.cu
+cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, int *prod, int *rc, Counters *ctr);
+cudaError_t launch_bin_scatter(const LaunchCtx &lc, bool numeric, int m, const int *prod, const int *rc,
+                               const BinOffsets &offs, Counters *ctr, int *queue);
+cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *prod, const int *rc, int64_t *rowoff64,
+                        int *rowptr32, long long *blocksums, Counters *ctr);
+size_t scan_blocksum_count(int m);
+// stage_small.cu
+cudaError_t launch_sym_esc(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B, int *rc);
+cudaError_t launch_num_single(const LaunchCtx &lc, int dtype, const int *queue, int count, Csr A, Csr B,
+                              const int64_t *rowoff, int *colC, void *valC);
+cudaError_t launch_num_esc(const LaunchCtx &lc, int dtype, const int *queue, int count, int n, Csr A, Csr B,
+                           const int64_t *rowoff, int *colC, void *valC);
+// stage_symbolic.cu
+cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B, int *rc);
+cudaError_t launch_sym_large(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B, int *rc,
+                             unsigned *bitmap_scratch, int scratch_blocks);
+// stage_numeric_f32.cu / stage_numeric_f64.cu
+cudaError_t launch_num_hash_f32(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B,
+                                const int64_t *rowoff, int *colC, float *valC);
+cudaError_t launch_num_hash_f64(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B,
+                                const int64_t *rowoff, int *colC, double *valC);
+cudaError_t launch_num_large_f32(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B,
+                                 const int64_t *rowoff, int *colC, float *valC, unsigned *bitmap_scratch,
+                                 int *prefix_scratch, int scratch_blocks);
+cudaError_t launch_num_large_f64(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B,
+                                 const int64_t *rowoff, int *colC, double *valC, unsigned *bitmap_scratch,
+                                 int *prefix_scratch, int scratch_blocks);
+int large_scratch_blocks(int sm_count);
+
+}  // namespace bhb

@@ -1,0 +1,594 @@
+// context.cu -- the C-ABI (include/bhsparse_b200.h) and the host orchestration of the
+// device pipeline.  Counterpart of bhsparse::spgemm_cuda (SpGEMM_cuda/bhsparse.h:297-339)
+// and of the memory management in bhsparse_cuda (bhsparse_cuda.h:121-203, 285-301,
+// 2783-2811, 3006-3020).  Host <-> device traffic inside one spgemm call: two reads of a
+// 300-byte counter block (bin sizes; nnz(C)) -- the reference has >= 8 blocking copies of
+// O(m) data plus 3 per merge round.
+#include "../../include/bhsparse_b200.h"
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+using namespace bhb;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes, size_t *total)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) {
+            cudaFree(p);
+            *total -= cap;
+            p = nullptr;
+            cap = 0;
+        }
+        // round up to 256 B; grow-only cache, released by free_mem
+        size_t want = (bytes + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        cap = want;
+        *total += cap;
+        return cudaSuccess;
+    }
+    void release(size_t *total)
+    {
+        if (p) {
+            cudaFree(p);
+            *total -= cap;
+        }
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const
+    {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+}  // namespace
+
+struct bhb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    char name[256] = {0};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // operands
+    bool have_data = false;
+    bool borrowed = false;
+    int dtype = BHB200_DTYPE_F64;
+    int m = 0, k = 0, n = 0, nnzA = 0, nnzB = 0;
+    DevBuf a_rowptr, a_col, a_val, b_rowptr, b_col, b_val;
+    Csr A{nullptr, nullptr, nullptr}, B{nullptr, nullptr, nullptr};
+
+    // workspace (grow-only, reused across calls)
+    DevBuf prod, rc, queue, rowoff64, rowptr32, blocksums, counters, bitmap, prefix;
+    size_t bitmap_zeroed_bytes = 0;
+    DevBuf colC, valC;
+    Counters *h_ctr = nullptr;   // pinned
+    size_t dev_bytes = 0;
+
+    bool have_C = false;
+    int64_t nnzC = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timing_valid = false;
+    int launches = 0;
+    bhb200_stats stats;
+};
+
+namespace {
+
+int fail(bhb200_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) {
+            c->err += ": ";
+            c->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CU(call, what)                                                            \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) {                                                 \
+            cudaGetLastError();                                                   \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? BHB200_ERR_ALLOC  \
+                                                              : BHB200_ERR_CUDA,  \
+                        what, e__);                                               \
+        }                                                                         \
+    } while (0)
+
+size_t vsize(int dtype)
+{
+    return dtype == BHB200_DTYPE_F64 ? 8 : 4;
+}
+
+void release_operands(bhb200_ctx *ctx)
+{
+    ctx->a_rowptr.release(&ctx->dev_bytes);
+    ctx->a_col.release(&ctx->dev_bytes);
+    ctx->a_val.release(&ctx->dev_bytes);
+    ctx->b_rowptr.release(&ctx->dev_bytes);
+    ctx->b_col.release(&ctx->dev_bytes);
+    ctx->b_val.release(&ctx->dev_bytes);
+    ctx->A = Csr{nullptr, nullptr, nullptr};
+    ctx->B = Csr{nullptr, nullptr, nullptr};
+    ctx->have_data = false;
+    ctx->borrowed = false;
+    ctx->have_C = false;
+    ctx->nnzC = 0;
+}
+
+int check_dims(bhb200_ctx *ctx, int m, int k, int n, int nnzA, int nnzB, const void *valA, const int32_t *rowptrA,
+               const int32_t *colA, const void *valB, const int32_t *rowptrB, const int32_t *colB)
+{
+    if (m < 0 || k < 0 || n < 0 || nnzA < 0 || nnzB < 0) return fail(ctx, BHB200_ERR_INVALID, "negative dimension");
+    if (!rowptrA || !rowptrB) return fail(ctx, BHB200_ERR_INVALID, "null row pointer array");
+    if (nnzA > 0 && (!colA || !valA)) return fail(ctx, BHB200_ERR_INVALID, "null A arrays");
+    if (nnzB > 0 && (!colB || !valB)) return fail(ctx, BHB200_ERR_INVALID, "null B arrays");
+    return BHB200_SUCCESS;
+}
+
+int init_host(bhb200_ctx *ctx, int dtype, int m, int k, int n, int nnzA, const void *valA, const int32_t *rowptrA,
+              const int32_t *colA, int nnzB, const void *valB, const int32_t *rowptrB, const int32_t *colB)
+{
+    if (!ctx) return BHB200_ERR_INVALID;
+    int rc = check_dims(ctx, m, k, n, nnzA, nnzB, valA, rowptrA, colA, valB, rowptrB, colB);
+    if (rc) return rc;
+    if (rowptrA[0] != 0 || rowptrA[m] != nnzA) return fail(ctx, BHB200_ERR_INVALID, "rowptrA does not span [0, nnzA]");
+    if (rowptrB[0] != 0 || rowptrB[k] != nnzB) return fail(ctx, BHB200_ERR_INVALID, "rowptrB does not span [0, nnzB]");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (ctx->borrowed) release_operands(ctx);
+    const size_t vs = vsize(dtype);
+    CU(ctx->a_rowptr.reserve((size_t)(m + 1) * 4, &ctx->dev_bytes), "alloc rowptrA");
+    CU(ctx->a_col.reserve((size_t)nnzA * 4 + 4, &ctx->dev_bytes), "alloc colA");
+    CU(ctx->a_val.reserve((size_t)nnzA * vs + 8, &ctx->dev_bytes), "alloc valA");
+    CU(ctx->b_rowptr.reserve((size_t)(k + 1) * 4, &ctx->dev_bytes), "alloc rowptrB");
+    CU(ctx->b_col.reserve((size_t)nnzB * 4 + 4, &ctx->dev_bytes), "alloc colB");
+    CU(ctx->b_val.reserve((size_t)nnzB * vs + 8, &ctx->dev_bytes), "alloc valB");
+    cudaStream_t s = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->a_rowptr.p, rowptrA, (size_t)(m + 1) * 4, cudaMemcpyHostToDevice, s), "H2D rowptrA");
+    CU(cudaMemcpyAsync(ctx->b_rowptr.p, rowptrB, (size_t)(k + 1) * 4, cudaMemcpyHostToDevice, s), "H2D rowptrB");
+    if (nnzA > 0) {
+        CU(cudaMemcpyAsync(ctx->a_col.p, colA, (size_t)nnzA * 4, cudaMemcpyHostToDevice, s), "H2D colA");
+        CU(cudaMemcpyAsync(ctx->a_val.p, valA, (size_t)nnzA * vs, cudaMemcpyHostToDevice, s), "H2D valA");
+    }
+    if (nnzB > 0) {
+        CU(cudaMemcpyAsync(ctx->b_col.p, colB, (size_t)nnzB * 4, cudaMemcpyHostToDevice, s), "H2D colB");
+        CU(cudaMemcpyAsync(ctx->b_val.p, valB, (size_t)nnzB * vs, cudaMemcpyHostToDevice, s), "H2D valB");
+    }
+    CU(cudaStreamSynchronize(s), "H2D operands");
+    ctx->A = Csr{ctx->a_rowptr.as<int>(), ctx->a_col.as<int>(), ctx->a_val.p};
+    ctx->B = Csr{ctx->b_rowptr.as<int>(), ctx->b_col.as<int>(), ctx->b_val.p};
+    ctx->dtype = dtype;
+    ctx->m = m;
+    ctx->k = k;
+    ctx->n = n;
+    ctx->nnzA = nnzA;
+    ctx->nnzB = nnzB;
+    ctx->have_data = true;
+    ctx->borrowed = false;
+    ctx->have_C = false;
+    ctx->nnzC = 0;
+    return BHB200_SUCCESS;
+}
+
+int reserve_workspace(bhb200_ctx *ctx)
+{
+    const size_t m1 = (size_t)ctx->m + 1;
+    CU(ctx->prod.reserve(m1 * 4, &ctx->dev_bytes), "alloc row products");
+    CU(ctx->rc.reserve(m1 * 4, &ctx->dev_bytes), "alloc row counts");
+    CU(ctx->queue.reserve(m1 * 4, &ctx->dev_bytes), "alloc row queue");
+    CU(ctx->rowoff64.reserve(m1 * 8, &ctx->dev_bytes), "alloc rowptrC64");
+    CU(ctx->rowptr32.reserve(m1 * 4, &ctx->dev_bytes), "alloc rowptrC");
+    CU(ctx->blocksums.reserve((scan_blocksum_count(ctx->m) + 1) * 8, &ctx->dev_bytes), "alloc scan sums");
+    CU(ctx->counters.reserve(sizeof(Counters), &ctx->dev_bytes), "alloc counters");
+    return BHB200_SUCCESS;
+}
+
+// scratch of the global-bitmap kernels: one n-bit bitmap (+ one int prefix per word)
+// per resident CTA, kept all-zero between uses
+int reserve_large_scratch(bhb200_ctx *ctx, bool need_prefix)
+{
+    const size_t nwords = ((size_t)ctx->n + 31) / 32;
+    const size_t blocks = (size_t)large_scratch_blocks(ctx->sm_count);
+    const size_t bytes = nwords * blocks * 4;
+    if (bytes > ctx->bitmap.cap) ctx->bitmap_zeroed_bytes = 0;
+    CU(ctx->bitmap.reserve(bytes, &ctx->dev_bytes), "alloc bitmap scratch");
+    if (ctx->bitmap_zeroed_bytes < bytes) {
+        CU(cudaMemsetAsync(ctx->bitmap.p, 0, ctx->bitmap.cap, ctx->stream), "zero bitmap scratch");
+        ctx->bitmap_zeroed_bytes = ctx->bitmap.cap;
+    }
+    if (need_prefix) CU(ctx->prefix.reserve(bytes, &ctx->dev_bytes), "alloc prefix scratch");
+    return BHB200_SUCCESS;
+}
+
+void offsets_from_counts(const int *counts, BinOffsets &o)
+{
+    int acc = 0;
+    for (int b = 0; b < MAX_BINS; ++b) {
+        o.off[b] = acc;
+        acc += counts[b];
+    }
+    o.off[MAX_BINS] = acc;
+}
+
+}  // namespace
+
+// ============================================================================
+extern "C" {
+
+const char *bhb200_version(void)
+{
+    return "bhsparse_b200 0.1.0 sm_100a";
+}
+
+int bhb200_create(bhb200_ctx **out, int device)
+{
+    if (!out) return BHB200_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return BHB200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) return BHB200_ERR_NO_DEVICE;
+    bhb200_ctx *ctx = new (std::nothrow) bhb200_ctx();
+    if (!ctx) return BHB200_ERR_ALLOC;
+    ctx->device = device;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return BHB200_ERR_NO_DEVICE;
+    }
+    if (prop.major < 10) {
+        // the kernels are built for sm_100a only; there is no fallback path
+        delete ctx;
+        return BHB200_ERR_NO_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->h_ctr, sizeof(Counters), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return BHB200_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    for (auto &ev : ctx->ev) {
+        if (cudaEventCreate(&ev) != cudaSuccess) {
+            cudaGetLastError();
+            delete ctx;
+            return BHB200_ERR_CUDA;
+        }
+    }
+    *out = ctx;
+    return BHB200_SUCCESS;
+}
+
+int bhb200_free_mem(bhb200_ctx *ctx)
+{
+    if (!ctx) return BHB200_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    release_operands(ctx);
+    DevBuf *bufs[] = {&ctx->prod, &ctx->rc, &ctx->queue, &ctx->rowoff64, &ctx->rowptr32, &ctx->blocksums,
+                      &ctx->counters, &ctx->bitmap, &ctx->prefix, &ctx->colC, &ctx->valC};
+    for (DevBuf *b : bufs) b->release(&ctx->dev_bytes);
+    ctx->bitmap_zeroed_bytes = 0;
+    cudaGetLastError();
+    return BHB200_SUCCESS;
+}
+
+int bhb200_destroy(bhb200_ctx *ctx)
+{
+    if (!ctx) return BHB200_ERR_INVALID;
+    bhb200_free_mem(ctx);
+    for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    cudaGetLastError();
+    delete ctx;
+    return BHB200_SUCCESS;
+}
+
+int bhb200_set_stream(bhb200_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return BHB200_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return BHB200_SUCCESS;
+}
+
+const char *bhb200_last_error(const bhb200_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : "null context";
+}
+const char *bhb200_device_name(const bhb200_ctx *ctx)
+{
+    return ctx ? ctx->name : "";
+}
+int bhb200_sm_count(const bhb200_ctx *ctx)
+{
+    return ctx ? ctx->sm_count : 0;
+}
+
+int bhb200_init_data_f64(bhb200_ctx *ctx, int m, int k, int n, int nnzA, const double *valA, const int32_t *rowptrA,
+                         const int32_t *colA, int nnzB, const double *valB, const int32_t *rowptrB,
+                         const int32_t *colB)
+{
+    return init_host(ctx, BHB200_DTYPE_F64, m, k, n, nnzA, valA, rowptrA, colA, nnzB, valB, rowptrB, colB);
+}
+int bhb200_init_data_f32(bhb200_ctx *ctx, int m, int k, int n, int nnzA, const float *valA, const int32_t *rowptrA,
+                         const int32_t *colA, int nnzB, const float *valB, const int32_t *rowptrB,
+                         const int32_t *colB)
+{
+    return init_host(ctx, BHB200_DTYPE_F32, m, k, n, nnzA, valA, rowptrA, colA, nnzB, valB, rowptrB, colB);
+}
+
+int bhb200_init_data_device(bhb200_ctx *ctx, int dtype, int m, int k, int n, int nnzA, const void *valA,
+                            const int32_t *rowptrA, const int32_t *colA, int nnzB, const void *valB,
+                            const int32_t *rowptrB, const int32_t *colB)
+{
+    if (!ctx) return BHB200_ERR_INVALID;
+    if (dtype != BHB200_DTYPE_F32 && dtype != BHB200_DTYPE_F64) return fail(ctx, BHB200_ERR_INVALID, "bad dtype");
+    int rc = check_dims(ctx, m, k, n, nnzA, nnzB, valA, rowptrA, colA, valB, rowptrB, colB);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    release_operands(ctx);
+    ctx->A = Csr{rowptrA, colA, valA};
+    ctx->B = Csr{rowptrB, colB, valB};
+    ctx->dtype = dtype;
+    ctx->m = m;
+    ctx->k = k;
+    ctx->n = n;
+    ctx->nnzA = nnzA;
+    ctx->nnzB = nnzB;
+    ctx->have_data = true;
+    ctx->borrowed = true;
+    return BHB200_SUCCESS;
+}
+
+int bhb200_warmup(bhb200_ctx *ctx)
+{
+    if (!ctx || !ctx->have_data) return fail(ctx, BHB200_ERR_INVALID, "warmup before initData");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (ctx->m == 0) return BHB200_SUCCESS;
+    int rc = reserve_workspace(ctx);
+    if (rc) return rc;
+    LaunchCtx lc{ctx->stream, ctx->sm_count, &ctx->launches};
+    CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), ctx->stream), "zero counters");
+    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->prod.as<int>(), ctx->rc.as<int>(),
+                           ctx->counters.as<Counters>()),
+       "row products kernel");
+    ctx->have_C = false;
+    return BHB200_SUCCESS;
+}
+
+int bhb200_spgemm(bhb200_ctx *ctx)
+{
+    if (!ctx || !ctx->have_data) return fail(ctx, BHB200_ERR_INVALID, "spgemm before initData");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ctx->have_C = false;
+    ctx->timing_valid = false;
+    ctx->launches = 0;
+    bhb200_stats &st = ctx->stats;
+    memset(&st, 0, sizeof(st));
+    st.m = ctx->m;
+    st.k = ctx->k;
+    st.n = ctx->n;
+    st.nnzA = ctx->nnzA;
+    st.nnzB = ctx->nnzB;
+    st.dtype = ctx->dtype;
+    const size_t vs = vsize(ctx->dtype);
+    cudaStream_t s = ctx->stream;
+    int rc = reserve_workspace(ctx);
+    if (rc) return rc;
+    LaunchCtx lc{s, ctx->sm_count, &ctx->launches};
+    Counters *d_ctr = ctx->counters.as<Counters>();
+    int *prod = ctx->prod.as<int>();
+    int *rcnt = ctx->rc.as<int>();
+    int *queue = ctx->queue.as<int>();
+    int64_t *rowoff = ctx->rowoff64.as<int64_t>();
+
+    // ---- stage 1: upper bound per row + symbolic bins ----
+    CU(cudaEventRecord(ctx->ev[0], s), "event");
+    CU(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s), "zero counters");
+    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, prod, rcnt, d_ctr), "row products kernel");
+    CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
+    CU(cudaStreamSynchronize(s), "stage 1");
+    Counters hc = *ctx->h_ctr;
+    if (hc.row_overflow) return fail(ctx, BHB200_ERR_OVERFLOW, "a row has more than INT32_MAX intermediate products");
+    st.products = (int64_t)hc.products;
+    st.max_row_products = hc.max_row_products;
+    for (int b = 0; b < BHB200_NUM_SYM_BINS && b < MAX_BINS; ++b) st.sym_bin_rows[b] = hc.sym_bin[b];
+    // lanes per row group: follow the average length of the B rows actually referenced
+    const double avg_b = ctx->nnzA > 0 ? (double)hc.products / (double)ctx->nnzA : 0.0;
+    const int G = avg_b <= 10.0 ? 8 : 32;
+    BinOffsets so;
+    offsets_from_counts(hc.sym_bin, so);
+    CU(launch_bin_scatter(lc, false, ctx->m, prod, rcnt, so, d_ctr, queue), "symbolic bin scatter");
+    CU(cudaEventRecord(ctx->ev[1], s), "event");
+
+    // ---- stage 2: symbolic, one launch per non-empty bin ----
+    CU(launch_sym_esc(lc, queue + so.off[SB_ESC], hc.sym_bin[SB_ESC], ctx->n, ctx->A, ctx->B, rcnt), "symbolic ESC");
+    for (int b = SB_G128; b <= SB_B32768; ++b)
+        CU(launch_sym_hash(lc, b, G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, rcnt), "symbolic hash");
+    if (hc.sym_bin[SB_LARGE] > 0) {
+        rc = reserve_large_scratch(ctx, false);
+        if (rc) return rc;
+        CU(launch_sym_large(lc, queue + so.off[SB_LARGE], hc.sym_bin[SB_LARGE], ctx->n, ctx->A, ctx->B, rcnt,
+                            ctx->bitmap.as<unsigned>(), large_scratch_blocks(ctx->sm_count)),
+           "symbolic large");
+    }
+    CU(cudaEventRecord(ctx->ev[2], s), "event");
+
+    // ---- stage 3: row pointers, numeric bins, exact allocation of C ----
+    CU(launch_scan(lc, ctx->m, prod, rcnt, rowoff, ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
+       "row pointer scan");
+    CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
+    CU(cudaStreamSynchronize(s), "stage 2/3");
+    hc = *ctx->h_ctr;
+    ctx->nnzC = (int64_t)hc.nnzC;
+    st.nnzC = ctx->nnzC;
+    for (int b = 0; b < BHB200_NUM_NUM_BINS && b < MAX_BINS; ++b) st.num_bin_rows[b] = hc.num_bin[b];
+    CU(ctx->colC.reserve((size_t)ctx->nnzC * 4 + 16, &ctx->dev_bytes), "alloc colC");
+    CU(ctx->valC.reserve((size_t)ctx->nnzC * vs + 16, &ctx->dev_bytes), "alloc valC");
+    BinOffsets no;
+    offsets_from_counts(hc.num_bin, no);
+    CU(launch_bin_scatter(lc, true, ctx->m, prod, rcnt, no, d_ctr, queue), "numeric bin scatter");
+    CU(cudaEventRecord(ctx->ev[3], s), "event");
+
+    // ---- stage 4: numeric, C written in place ----
+    int *colC = ctx->colC.as<int>();
+    void *valC = ctx->valC.p;
+    CU(launch_num_single(lc, ctx->dtype, queue + no.off[NB_ONE], hc.num_bin[NB_ONE], ctx->A, ctx->B, rowoff, colC, valC),
+       "numeric single");
+    CU(launch_num_esc(lc, ctx->dtype, queue + no.off[NB_ESC], hc.num_bin[NB_ESC], ctx->n, ctx->A, ctx->B, rowoff, colC, valC),
+       "numeric ESC");
+    for (int b = NB_G64; b <= NB_B16384; ++b) {
+        if (ctx->dtype == BHB200_DTYPE_F64)
+            CU(launch_num_hash_f64(lc, b, G, queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rowoff, colC, (double *)valC),
+               "numeric hash f64");
+        else
+            CU(launch_num_hash_f32(lc, b, G, queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rowoff, colC, (float *)valC),
+               "numeric hash f32");
+    }
+    if (hc.num_bin[NB_LARGE] > 0) {
+        rc = reserve_large_scratch(ctx, true);
+        if (rc) return rc;
+        const int sb = large_scratch_blocks(ctx->sm_count);
+        if (ctx->dtype == BHB200_DTYPE_F64)
+            CU(launch_num_large_f64(lc, queue + no.off[NB_LARGE], hc.num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
+                                    (double *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
+               "numeric large f64");
+        else
+            CU(launch_num_large_f32(lc, queue + no.off[NB_LARGE], hc.num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
+                                    (float *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
+               "numeric large f32");
+    }
+    CU(cudaEventRecord(ctx->ev[4], s), "event");
+
+    st.kernel_launches = ctx->launches;
+    const int64_t v = (int64_t)vs;
+    const int64_t m1 = (int64_t)ctx->m + 1;
+    st.bytes_algorithmic = (m1 * 4 + (int64_t)ctx->nnzA * (4 + v)) + ((int64_t)ctx->nnzA * 8 + st.products * (4 + v)) +
+                           (m1 * 4 + ctx->nnzC * (4 + v));
+    st.bytes_compulsory = (m1 * 4 + (int64_t)ctx->nnzA * (4 + v)) + (((int64_t)ctx->k + 1) * 4 + (int64_t)ctx->nnzB * (4 + v)) +
+                          (m1 * 4 + ctx->nnzC * (4 + v));
+    st.workspace_bytes = (int64_t)ctx->dev_bytes;
+    ctx->have_C = true;
+    ctx->timing_valid = true;
+    return BHB200_SUCCESS;
+}
+
+int bhb200_synchronize(bhb200_ctx *ctx)
+{
+    if (!ctx) return BHB200_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CU(cudaStreamSynchronize(ctx->stream), "synchronize");
+    return BHB200_SUCCESS;
+}
+
+int64_t bhb200_get_nnzC(const bhb200_ctx *ctx)
+{
+    return (ctx && ctx->have_C) ? ctx->nnzC : -1;
+}
+
+static int get_C_any(bhb200_ctx *ctx, int dtype, int32_t *rowptrC, int32_t *colC, void *valC)
+{
+    if (!ctx || !ctx->have_C) return fail(ctx, BHB200_ERR_INVALID, "get_C before spgemm");
+    if (dtype != ctx->dtype) return fail(ctx, BHB200_ERR_INVALID, "get_C dtype differs from initData dtype");
+    if (ctx->nnzC > 0x7fffffffLL) return fail(ctx, BHB200_ERR_OVERFLOW, "nnz(C) exceeds INT32_MAX; use the int64 row pointers");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t s = ctx->stream;
+    if (rowptrC)
+        CU(cudaMemcpyAsync(rowptrC, ctx->rowptr32.p, ((size_t)ctx->m + 1) * 4, cudaMemcpyDeviceToHost, s), "D2H rowptrC");
+    if (colC && ctx->nnzC > 0)
+        CU(cudaMemcpyAsync(colC, ctx->colC.p, (size_t)ctx->nnzC * 4, cudaMemcpyDeviceToHost, s), "D2H colC");
+    if (valC && ctx->nnzC > 0)
+        CU(cudaMemcpyAsync(valC, ctx->valC.p, (size_t)ctx->nnzC * vsize(dtype), cudaMemcpyDeviceToHost, s), "D2H valC");
+    CU(cudaStreamSynchronize(s), "D2H C");
+    return BHB200_SUCCESS;
+}
+
+int bhb200_get_C_f64(bhb200_ctx *ctx, int32_t *rowptrC, int32_t *colC, double *valC)
+{
+    return get_C_any(ctx, BHB200_DTYPE_F64, rowptrC, colC, valC);
+}
+int bhb200_get_C_f32(bhb200_ctx *ctx, int32_t *rowptrC, int32_t *colC, float *valC)
+{
+    return get_C_any(ctx, BHB200_DTYPE_F32, rowptrC, colC, valC);
+}
+
+int bhb200_get_rowptrC_i64(bhb200_ctx *ctx, int64_t *rowptrC64)
+{
+    if (!ctx || !ctx->have_C) return fail(ctx, BHB200_ERR_INVALID, "get_rowptrC before spgemm");
+    if (!rowptrC64) return fail(ctx, BHB200_ERR_INVALID, "null pointer");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CU(cudaMemcpyAsync(rowptrC64, ctx->rowoff64.p, ((size_t)ctx->m + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H rowptrC64");
+    CU(cudaStreamSynchronize(ctx->stream), "D2H rowptrC64");
+    return BHB200_SUCCESS;
+}
+
+int bhb200_get_C_device(bhb200_ctx *ctx, const int32_t **rowptr32, const int64_t **rowptr64, const int32_t **colC,
+                        const void **valC)
+{
+    if (!ctx || !ctx->have_C) return fail(ctx, BHB200_ERR_INVALID, "get_C_device before spgemm");
+    if (rowptr32) *rowptr32 = ctx->nnzC > 0x7fffffffLL ? nullptr : ctx->rowptr32.as<int32_t>();
+    if (rowptr64) *rowptr64 = ctx->rowoff64.as<int64_t>();
+    if (colC) *colC = ctx->colC.as<int32_t>();
+    if (valC) *valC = ctx->valC.p;
+    return BHB200_SUCCESS;
+}
+
+int bhb200_get_row_products(bhb200_ctx *ctx, int32_t *row_products)
+{
+    if (!ctx || !ctx->have_data || !ctx->prod.p) return fail(ctx, BHB200_ERR_INVALID, "no row products yet");
+    if (!row_products) return fail(ctx, BHB200_ERR_INVALID, "null pointer");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (ctx->m > 0)
+        CU(cudaMemcpyAsync(row_products, ctx->prod.p, (size_t)ctx->m * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H row products");
+    CU(cudaStreamSynchronize(ctx->stream), "D2H row products");
+    return BHB200_SUCCESS;
+}
+
+int bhb200_get_stats(const bhb200_ctx *cctx, bhb200_stats *out)
+{
+    bhb200_ctx *ctx = const_cast<bhb200_ctx *>(cctx);
+    if (!ctx || !out) return BHB200_ERR_INVALID;
+    if (ctx->timing_valid) {
+        CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+        CU(cudaEventSynchronize(ctx->ev[4]), "event sync");
+        bhb200_stats &st = ctx->stats;
+        cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[4]);
+        cudaEventElapsedTime(&st.ms_count, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&st.ms_symbolic, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&st.ms_scan, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&st.ms_numeric, ctx->ev[3], ctx->ev[4]);
+    }
+    *out = ctx->stats;
+    return BHB200_SUCCESS;
+}
+
+}  // extern "C"

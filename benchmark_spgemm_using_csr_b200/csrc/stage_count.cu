@@ -1,0 +1,305 @@
+// stage_count.cu -- stage 1 (per-row upper bound + binning) and the row-pointer
+// scan.  Replaces compute_nnzCt_cudakernel (SpGEMM_cuda/bhsparse_cuda.h:210-237),
+// the HOST passes of bhsparse::statistics (bhsparse.h:365-481) and the HOST scan
+// of bhsparse_cuda::create_C (bhsparse_cuda.h:2783-2811) with device kernels.
+#include "common.cuh"
+
+namespace bhb {
+
+// ---------------------------------------------------------------------------
+// k_row_products: G lanes per row of A.  prod[i] = sum_{k in A_i} len(B_k).
+// The reference uses one thread per row (uncoalesced colA reads); here a group
+// of G lanes reads G consecutive column indices per step and the rowptrB pair
+// gathers of a warp are issued together.  Also builds the symbolic-bin
+// histogram, the product total (int64) and settles rows with p <= 1.
+// ---------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) k_row_products(const int m, const int *__restrict__ rowptrA,
+                                                      const int *__restrict__ colA,
+                                                      const int *__restrict__ rowptrB, int *__restrict__ prod,
+                                                      int *__restrict__ rc, Counters *__restrict__ ctr)
+{
+    __shared__ int s_hist[MAX_BINS];
+    __shared__ unsigned long long s_total;
+    __shared__ int s_max, s_ovf;
+    if (threadIdx.x < MAX_BINS) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        s_total = 0ull;
+        s_max = 0;
+        s_ovf = 0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const int groups_per_block = blockDim.x / G;
+    const long long stride = (long long)gridDim.x * groups_per_block;
+    unsigned long long my_total = 0ull;
+    int my_max = 0;
+
+    for (long long r = (long long)blockIdx.x * groups_per_block + threadIdx.x / G; r < m; r += stride) {
+        const int row = (int)r;
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        long long s = 0;
+        for (int j = a0 + gl; j < a1; j += G) {
+            const int k = colA[j];
+            s += (long long)(__ldg(rowptrB + k + 1) - __ldg(rowptrB + k));
+        }
+#pragma unroll
+        for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(gmask, s, d, G);
+        if (gl == 0) {
+            int p;
+            if (s > 0x7fffffffLL) {
+                p = 0x7fffffff;
+                s_ovf = 1;
+            } else {
+                p = (int)s;
+            }
+            prod[row] = p;
+            if (p <= 1) rc[row] = p;
+            atomicAdd(&s_hist[sym_bin_of(p)], 1);
+            my_total += (unsigned long long)s;
+            my_max = max(my_max, p);
+        }
+    }
+    // block reduction of totals
+    my_total = warp_sum(my_total);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_max = max(my_max, __shfl_xor_sync(FULL, my_max, d));
+    if (lane == 0) {
+        atomicAdd(&s_total, my_total);
+        atomicMax(&s_max, my_max);
+    }
+    __syncthreads();
+    if (threadIdx.x < MAX_BINS && s_hist[threadIdx.x]) atomicAdd(&ctr->sym_bin[threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        if (s_total) atomicAdd(&ctr->products, s_total);
+        atomicMax(&ctr->max_row_products, s_max);
+        if (s_ovf) ctr->row_overflow = 1;
+    }
+}
+
+cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, int *prod, int *rc, Counters *ctr)
+{
+    if (m <= 0) return cudaSuccess;
+    const double avg = (double)nnzA / (double)m;
+    const int threads = 256;
+    int G = avg <= 3.0 ? 2 : avg <= 6.0 ? 4 : avg <= 12.0 ? 8 : avg <= 24.0 ? 16 : 32;
+    const long long rows_per_block = threads / G;
+    long long blocks = (m + rows_per_block - 1) / rows_per_block;
+    const long long cap = (long long)lc.sm_count * 64;
+    if (blocks > cap) blocks = cap;
+    ++*lc.launches;
+    switch (G) {
+    case 2: k_row_products<2><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
+    case 4: k_row_products<4><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
+    case 8: k_row_products<8><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
+    case 16: k_row_products<16><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
+    default: k_row_products<32><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// k_bin_scatter: rows -> queue, bins contiguous (offsets come from the bin
+// histogram; the host only turns 13 counts into 13 offsets).  One block handles
+// a contiguous chunk of rows and claims one range per bin with a single global
+// atomic, so rows stay in ascending order per bin up to block granularity --
+// neighbouring rows (which share rows of B) are processed by neighbouring warps.
+// Replaces the second host pass of bhsparse::statistics (bhsparse.h:434-478).
+// ---------------------------------------------------------------------------
+constexpr int SCATTER_ITEMS = 4;
+template <bool NUMERIC>
+__global__ void __launch_bounds__(256) k_bin_scatter(const int m, const int *__restrict__ prod,
+                                                     const int *__restrict__ rc, const BinOffsets offs,
+                                                     int *__restrict__ cursor, int *__restrict__ queue)
+{
+    __shared__ int s_cnt[MAX_BINS];
+    __shared__ int s_base[MAX_BINS];
+    if (threadIdx.x < MAX_BINS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long long chunk0 = (long long)blockIdx.x * blockDim.x * SCATTER_ITEMS;
+    int bin[SCATTER_ITEMS], rank[SCATTER_ITEMS];
+#pragma unroll
+    for (int it = 0; it < SCATTER_ITEMS; ++it) {
+        const long long row = chunk0 + (long long)it * blockDim.x + threadIdx.x;
+        bin[it] = -1;
+        if (row < m) {
+            const int p = prod[row];
+            bin[it] = NUMERIC ? num_bin_of(p, rc[row]) : sym_bin_of(p);
+            rank[it] = atomicAdd(&s_cnt[bin[it]], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < MAX_BINS) {
+        const int c = s_cnt[threadIdx.x];
+        s_base[threadIdx.x] = c ? offs.off[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], c) : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < SCATTER_ITEMS; ++it) {
+        if (bin[it] >= 0) {
+            const long long row = chunk0 + (long long)it * blockDim.x + threadIdx.x;
+            queue[s_base[bin[it]] + rank[it]] = (int)row;
+        }
+    }
+}
+
+cudaError_t launch_bin_scatter(const LaunchCtx &lc, bool numeric, int m, const int *prod, const int *rc,
+                               const BinOffsets &offs, Counters *ctr, int *queue)
+{
+    if (m <= 0) return cudaSuccess;
+    const int threads = 256;
+    const long long per_block = (long long)threads * SCATTER_ITEMS;
+    const int blocks = (int)((m + per_block - 1) / per_block);
+    ++*lc.launches;
+    if (numeric)
+        k_bin_scatter<true><<<blocks, threads, 0, lc.stream>>>(m, prod, rc, offs, ctr->num_cursor, queue);
+    else
+        k_bin_scatter<false><<<blocks, threads, 0, lc.stream>>>(m, prod, rc, offs, ctr->sym_cursor, queue);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Row-pointer scan: rc[i] = nnz(C_i)  ->  rowoff64[0..m], rowptr32[0..m]
+// (three small kernels: chunk sums + numeric-bin histogram, scan of the chunk
+// sums, chunk-local scan + offset).  Replaces the D2H / host loop / H2D of
+// create_C (bhsparse_cuda.h:2787-2808).  Totals are int64; rowptr32 saturates.
+// ---------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+size_t scan_blocksum_count(int m)
+{
+    return (size_t)((m + SCAN_CHUNK - 1) / SCAN_CHUNK) + 1;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int m, const int *__restrict__ prod,
+                                                              const int *__restrict__ rc,
+                                                              long long *__restrict__ blocksums,
+                                                              Counters *__restrict__ ctr)
+{
+    __shared__ int s_hist[MAX_BINS];
+    __shared__ long long s_red[33];
+    if (threadIdx.x < MAX_BINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * SCAN_CHUNK;
+    long long s = 0;
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS; ++it) {
+        const long long i = base + (long long)it * SCAN_THREADS + threadIdx.x;
+        if (i < m) {
+            const int c = rc[i];
+            s += c;
+            atomicAdd(&s_hist[num_bin_of(prod[i], c)], 1);
+        }
+    }
+    const long long tot = block_sum(s, s_red);
+    if (threadIdx.x == 0) blocksums[blockIdx.x] = tot;
+    if (threadIdx.x < MAX_BINS && s_hist[threadIdx.x]) atomicAdd(&ctr->num_bin[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+// one block: exclusive scan of blocksums[0..nb) in place; total -> ctr->nnzC and blocksums[nb]
+__global__ void __launch_bounds__(1024) k_scan_blocks(const int nb, long long *__restrict__ blocksums,
+                                                      Counters *__restrict__ ctr)
+{
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const long long v = (i < nb) ? blocksums[i] : 0;
+        long long x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long y = __shfl_up_sync(FULL, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long y = __shfl_up_sync(FULL, w, d);
+                if (lane >= d) w += y;
+            }
+            s_warp[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const long long carry = s_carry;
+        const long long warp_off = warp ? s_warp[warp - 1] : 0;
+        if (i < nb) blocksums[i] = carry + warp_off + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        blocksums[nb] = s_carry;
+        ctr->nnzC = (unsigned long long)s_carry;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const int m, const int *__restrict__ rc,
+                                                             const long long *__restrict__ blocksums,
+                                                             const int nb, int64_t *__restrict__ rowoff64,
+                                                             int *__restrict__ rowptr32)
+{
+    __shared__ long long s_warp[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // each thread owns SCAN_ITEMS consecutive rows
+    const long long first = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    long long s = 0;
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS; ++it) {
+        const long long i = first + it;
+        v[it] = (i < m) ? rc[i] : 0;
+        s += v[it];
+    }
+    long long x = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    long long off = blocksums[blockIdx.x] + (x - s);
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS; ++it) {
+        const long long i = first + it;
+        if (i < m) {
+            rowoff64[i] = off;
+            rowptr32[i] = off > 0x7fffffffLL ? 0x7fffffff : (int)off;
+        }
+        off += v[it];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long tot = blocksums[nb];
+        rowoff64[m] = tot;
+        rowptr32[m] = tot > 0x7fffffffLL ? 0x7fffffff : (int)tot;
+    }
+}
+
+cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *prod, const int *rc, int64_t *rowoff64,
+                        int *rowptr32, long long *blocksums, Counters *ctr)
+{
+    const int nb = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (nb > 0) {
+        ++*lc.launches;
+        k_scan_reduce<<<nb, SCAN_THREADS, 0, lc.stream>>>(m, prod, rc, blocksums, ctr);
+    }
+    ++*lc.launches;
+    k_scan_blocks<<<1, 1024, 0, lc.stream>>>(nb, blocksums, ctr);
+    ++*lc.launches;
+    k_scan_write<<<nb > 0 ? nb : 1, SCAN_THREADS, 0, lc.stream>>>(m, rc, blocksums, nb, rowoff64, rowptr32);
+    return cudaGetLastError();
+}
+
+}  // namespace bhb

@@ -1,0 +1,395 @@
+// stage_numeric.cuh -- numeric kernels (hash accumulate, sort, write C in place),
+// instantiated for float in stage_numeric_f32.cu and double in stage_numeric_f64.cu.
+//
+// k_num_group<VT,G,LOG2T,R> : a group of G lanes owns a row: T-slot (column,value) table in
+//      shared memory, B rows streamed one per step (columns of one B row are distinct, so the
+//      value update needs no atomic -- shared-memory FP atomics are CAS loops on sm_100a).
+//      Then: compact the occupied columns, sort them (R>0: register bitonic network over
+//      warp shuffles; R==0: bitonic in shared memory), look each sorted column's value up
+//      again and store the row at rowptrC[row] with coalesced writes.
+//      Covers what ESC_bitonic_scan (bhsparse_cuda.h:1400-1518) and the first rounds of
+//      EM_mergepath (:1902-2157) do in the reference, for nnz(C_i) <= 1024.
+// k_num_block<VT,LOG2T>     : one CTA per row, nnz(C_i) <= 8192, same scheme with a CTA-wide
+//      table (up to 224 KB of shared memory) -- the rows the reference sends through
+//      EM_mergepath rounds 2..5 and EM_mergepath_global (:2270-2525).
+// k_num_large<VT>           : longer rows: rank of a column = popcount prefix of the row's
+//      column bitmap (global, L2 resident); products are accumulated straight into the
+//      final C row with red.global.add -- no spill, no re-allocation, no sort.
+#pragma once
+#include "common.cuh"
+
+namespace bhb {
+
+template <typename VT, int G, int LOG2T, int R>
+__global__ void __launch_bounds__(256)
+k_num_group(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
+            const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
+            const int *__restrict__ colB, const VT *__restrict__ valB, const int64_t *__restrict__ rowoff,
+            int *__restrict__ colC, VT *__restrict__ valC)
+{
+    constexpr int T = 1 << LOG2T;
+    constexpr int N = T / 2;                 // max nnz(C_i) of the bin
+    constexpr size_t PER_GROUP = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)N * 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x & (G - 1);
+    const int gib = threadIdx.x / G;
+    const int groups_per_block = blockDim.x / G;
+    const unsigned gmask = group_mask<G>(lane);
+    const int gshift = lane & ~(G - 1);
+    unsigned char *mine = smem_raw + (size_t)gib * PER_GROUP;
+    VT *vals = reinterpret_cast<VT *>(mine);
+    int *keys = reinterpret_cast<int *>(mine + (size_t)T * sizeof(VT));
+    int *sk = keys + T;
+
+    for (int q = blockIdx.x * groups_per_block + gib; q < count; q += gridDim.x * groups_per_block) {
+        const int row = queue[q];
+#pragma unroll 4
+        for (int s = gl; s < T; s += G) {
+            keys[s] = EMPTY_KEY;
+            vals[s] = VT(0);
+        }
+        __syncwarp(gmask);
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        for (int base = a0; base < a1; base += G) {
+            const int j = base + gl;
+            int bs = 0, be = 0;
+            VT av = VT(0);
+            if (j < a1) {
+                const int k = colA[j];
+                bs = rowptrB[k];
+                be = rowptrB[k + 1];
+                av = valA[j];
+            }
+            const int cnt = min(G, a1 - base);
+            for (int t = 0; t < cnt; ++t) {
+                const int s_bs = __shfl_sync(gmask, bs, t, G);
+                const int s_be = __shfl_sync(gmask, be, t, G);
+                const VT s_av = __shfl_sync(gmask, av, t, G);
+                for (int p = s_bs + gl; p < s_be; p += G) {
+                    const int c = colB[p];
+                    const VT v = s_av * valB[p];
+                    bool is_new;
+                    const int slot = table_insert<LOG2T>(keys, c, is_new);
+                    vals[slot] += v;
+                }
+                __syncwarp(gmask);   // the next B row may hit the same slots
+            }
+        }
+        // ---- compact the occupied columns into sk[0..cnt) ----
+        int cntc = 0;
+        for (int s0 = 0; s0 < T; s0 += G) {
+            const int k = keys[s0 + gl];
+            const bool occ = (k != EMPTY_KEY);
+            const unsigned bm = __ballot_sync(gmask, occ) >> gshift;
+            if (occ) sk[cntc + __popc(bm & ((1u << gl) - 1u))] = k;
+            cntc += __popc(bm);
+        }
+        __syncwarp(gmask);
+        // ---- sort ----
+        if constexpr (R > 0) {
+            constexpr int RR = R;
+            static_assert(G * RR == N, "register sort must cover the bin");
+            int x[RR];
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                const int i = gl * RR + r;
+                x[r] = (i < cntc) ? sk[i] : SORT_PAD;
+            }
+            bitonic_sort_regs<G, RR>(x, gl, gmask);
+            __syncwarp(gmask);
+#pragma unroll
+            for (int r = 0; r < RR; ++r) sk[gl * RR + r] = x[r];
+            __syncwarp(gmask);
+        } else {
+            const int np = next_pow2(cntc);
+            for (int i = cntc + gl; i < np; i += G) sk[i] = SORT_PAD;
+            __syncwarp(gmask);
+            bitonic_sort_smem_group<G>(sk, np, gl, gmask);
+        }
+        // ---- emit: sorted columns + their accumulated values, coalesced ----
+        const int64_t o = rowoff[row];
+        for (int i = gl; i < cntc; i += G) {
+            const int c = sk[i];
+            const int slot = table_find<LOG2T>(keys, c);
+            colC[o + i] = c;
+            valC[o + i] = vals[slot];
+        }
+        __syncwarp(gmask);
+    }
+}
+
+template <typename VT, int LOG2T>
+__global__ void __launch_bounds__(512)
+k_num_block(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
+            const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
+            const int *__restrict__ colB, const VT *__restrict__ valB, const int64_t *__restrict__ rowoff,
+            int *__restrict__ colC, VT *__restrict__ valC)
+{
+    constexpr int T = 1 << LOG2T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_cnt;
+    VT *vals = reinterpret_cast<VT *>(smem_raw);
+    int *keys = reinterpret_cast<int *>(smem_raw + (size_t)T * sizeof(VT));
+    int *sk = keys + T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int row = queue[q];
+        for (int s = threadIdx.x; s < T; s += blockDim.x) {
+            keys[s] = EMPTY_KEY;
+            vals[s] = VT(0);
+        }
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        for (int j = a0 + warp; j < a1; j += nwarps) {
+            const int k = colA[j];
+            const VT av = valA[j];
+            const int bs = rowptrB[k], be = rowptrB[k + 1];
+            for (int p = bs + lane; p < be; p += 32) {
+                const int c = colB[p];
+                const VT v = av * valB[p];
+                bool is_new;
+                const int slot = table_insert<LOG2T>(keys, c, is_new);
+                atomicAdd(&vals[slot], v);   // different warps may meet in one slot
+            }
+        }
+        __syncthreads();
+        // compact occupied columns (order irrelevant, sorted next)
+        for (int s0 = 0; s0 < T; s0 += blockDim.x) {
+            const int s = s0 + threadIdx.x;
+            const int k = (s < T) ? keys[s] : EMPTY_KEY;
+            const bool occ = (k != EMPTY_KEY);
+            const unsigned bm = __ballot_sync(FULL, occ);
+            int basepos = 0;
+            if (lane == 0 && bm) basepos = atomicAdd(&s_cnt, __popc(bm));
+            basepos = __shfl_sync(FULL, basepos, 0);
+            if (occ) sk[basepos + __popc(bm & ((1u << lane) - 1u))] = k;
+        }
+        __syncthreads();
+        const int cntc = s_cnt;
+        const int np = next_pow2(cntc);
+        for (int i = cntc + threadIdx.x; i < np; i += blockDim.x) sk[i] = SORT_PAD;
+        __syncthreads();
+        bitonic_sort_smem_block(sk, np);
+        const int64_t o = rowoff[row];
+        for (int i = threadIdx.x; i < cntc; i += blockDim.x) {
+            const int c = sk[i];
+            const int slot = table_find<LOG2T>(keys, c);
+            colC[o + i] = c;
+            valC[o + i] = vals[slot];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename VT>
+__global__ void __launch_bounds__(1024)
+k_num_large(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
+            const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
+            const int *__restrict__ colB, const VT *__restrict__ valB, const int64_t *__restrict__ rowoff,
+            int *__restrict__ colC, VT *__restrict__ valC, unsigned *__restrict__ bitmap_all,
+            int *__restrict__ prefix_all, const int nwords)
+{
+    __shared__ int s_red[33];
+    __shared__ int s_lo, s_hi;
+    unsigned *bm = bitmap_all + (size_t)blockIdx.x * nwords;
+    int *prefix = prefix_all + (size_t)blockIdx.x * nwords;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int row = queue[q];
+        if (threadIdx.x == 0) {
+            s_lo = 0x7fffffff;
+            s_hi = -1;
+        }
+        __syncthreads();
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        const int64_t o = rowoff[row];
+        const int nout = (int)(rowoff[row + 1] - o);
+        // ---- 1. mark the row's columns; zero the row's values ----
+        int wlo = 0x7fffffff, whi = -1;
+        for (int j = a0 + warp; j < a1; j += nwarps) {
+            const int k = colA[j];
+            const int bs = rowptrB[k], be = rowptrB[k + 1];
+            for (int p = bs + lane; p < be; p += 32) {
+                const int c = colB[p];
+                const int w = c >> 5;
+                atomicOr(&bm[w], 1u << (c & 31));
+                wlo = min(wlo, w);
+                whi = max(whi, w);
+            }
+        }
+        if (whi >= 0) {
+            atomicMin(&s_lo, wlo);
+            atomicMax(&s_hi, whi);
+        }
+        for (int i = threadIdx.x; i < nout; i += blockDim.x) valC[o + i] = VT(0);
+        __threadfence();
+        __syncthreads();
+        // ---- 2. exclusive popcount prefix over the touched word range ----
+        const int lo = s_lo, hi = s_hi;
+        const int nw = hi - lo + 1;
+        const int per = (nw + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int w0 = lo + (int)threadIdx.x * per;
+        const int w1 = min(w0 + per, hi + 1);
+        int mysum = 0;
+        for (int w = w0; w < w1; ++w) mysum += __popc(__ldcg(bm + w));
+        // block exclusive scan of mysum
+        {
+            int x = mysum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(FULL, x, d);
+                if (lane >= d) x += y;
+            }
+            if (lane == 31) s_red[warp] = x;
+            __syncthreads();
+            if (warp == 0) {
+                int wv = (lane < nwarps) ? s_red[lane] : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_up_sync(FULL, wv, d);
+                    if (lane >= d) wv += y;
+                }
+                s_red[lane] = wv;
+            }
+            __syncthreads();
+            mysum = (warp ? s_red[warp - 1] : 0) + x - mysum;   // exclusive prefix of this thread
+        }
+        int run = mysum;
+        for (int w = w0; w < w1; ++w) {
+            const unsigned bits = __ldcg(bm + w);
+            prefix[w] = run;
+            // columns of this word are final: write them now, in order
+            unsigned b = bits;
+            int r2 = run;
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                colC[o + r2] = (w << 5) | bit;
+                ++r2;
+            }
+            run += __popc(bits);
+        }
+        __threadfence();
+        __syncthreads();
+        // ---- 3. accumulate products at their rank ----
+        for (int j = a0 + warp; j < a1; j += nwarps) {
+            const int k = colA[j];
+            const VT av = valA[j];
+            const int bs = rowptrB[k], be = rowptrB[k + 1];
+            for (int p = bs + lane; p < be; p += 32) {
+                const int c = colB[p];
+                const int w = c >> 5;
+                const unsigned bits = __ldcg(bm + w);
+                const int pos = __ldcg(prefix + w) + __popc(bits & ((1u << (c & 31)) - 1u));
+                atomicAdd(&valC[o + pos], av * valB[p]);
+            }
+        }
+        __syncthreads();
+        // ---- 4. restore the all-zero bitmap ----
+        for (int w = lo + (int)threadIdx.x; w <= hi; w += blockDim.x) {
+            if (__ldcg(bm + w)) bm[w] = 0u;
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------
+template <typename VT, int G, int LOG2T, int R>
+static cudaError_t launch_num_group_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B,
+                                      const int64_t *rowoff, int *colC, VT *valC)
+{
+    constexpr int T = 1 << LOG2T;
+    constexpr size_t per_group = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)(T / 2) * 4;
+    int groups = (int)((56 * 1024) / per_group);
+    const int max_groups = 256 / G;
+    if (groups > max_groups) groups = max_groups;
+    const int min_groups = 32 / G;
+    if (groups < min_groups) groups = min_groups;
+    const int threads = groups * G;
+    const size_t smem = per_group * groups;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_num_group<VT, G, LOG2T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    long long blocks = ((long long)count + groups - 1) / groups;
+    int per_sm = (int)((200 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    const long long cap = (long long)lc.sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    ++*lc.launches;
+    k_num_group<VT, G, LOG2T, R><<<(int)blocks, threads, smem, lc.stream>>>(
+        queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col, (const VT *)B.val, rowoff, colC, valC);
+    return cudaGetLastError();
+}
+
+template <typename VT, int LOG2T>
+static cudaError_t launch_num_block_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B,
+                                      const int64_t *rowoff, int *colC, VT *valC)
+{
+    constexpr int T = 1 << LOG2T;
+    const size_t smem = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)(T / 2) * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_num_block<VT, LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    long long blocks = count;
+    const long long cap = (long long)lc.sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    ++*lc.launches;
+    k_num_block<VT, LOG2T><<<(int)blocks, 512, smem, lc.stream>>>(
+        queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col, (const VT *)B.val, rowoff, colC, valC);
+    return cudaGetLastError();
+}
+
+template <typename VT>
+static cudaError_t launch_num_hash_t(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B,
+                                     const int64_t *rowoff, int *colC, VT *valC)
+{
+    if (count <= 0) return cudaSuccess;
+    // register-sort widths: G=32 -> R = N/32; G=8 -> R = N/8 while <= 16, else shared-memory sort
+    switch (bin) {
+    case NB_G64:
+        return G == 8 ? launch_num_group_t<VT, 8, 6, 4>(lc, queue, count, A, B, rowoff, colC, valC)
+                      : launch_num_group_t<VT, 32, 6, 1>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_G128:
+        return G == 8 ? launch_num_group_t<VT, 8, 7, 8>(lc, queue, count, A, B, rowoff, colC, valC)
+                      : launch_num_group_t<VT, 32, 7, 2>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_G256:
+        return G == 8 ? launch_num_group_t<VT, 8, 8, 16>(lc, queue, count, A, B, rowoff, colC, valC)
+                      : launch_num_group_t<VT, 32, 8, 4>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_G512:
+        return G == 8 ? launch_num_group_t<VT, 8, 9, 0>(lc, queue, count, A, B, rowoff, colC, valC)
+                      : launch_num_group_t<VT, 32, 9, 8>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_G1024: return launch_num_group_t<VT, 32, 10, 16>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_G2048: return launch_num_group_t<VT, 32, 11, 0>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_B4096: return launch_num_block_t<VT, 12>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_B8192: return launch_num_block_t<VT, 13>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_B16384: return launch_num_block_t<VT, 14>(lc, queue, count, A, B, rowoff, colC, valC);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <typename VT>
+static cudaError_t launch_num_large_t(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B,
+                                      const int64_t *rowoff, int *colC, VT *valC, unsigned *bitmap_scratch,
+                                      int *prefix_scratch, int scratch_blocks)
+{
+    if (count <= 0) return cudaSuccess;
+    const int nwords = (n + 31) / 32;
+    const int blocks = count < scratch_blocks ? count : scratch_blocks;
+    ++*lc.launches;
+    k_num_large<VT><<<blocks, 1024, 0, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
+                                                    (const VT *)B.val, rowoff, colC, valC, bitmap_scratch,
+                                                    prefix_scratch, nwords);
+    return cudaGetLastError();
+}
+
+}  // namespace bhb

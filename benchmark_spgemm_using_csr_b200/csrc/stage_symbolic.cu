@@ -1,0 +1,243 @@
+// stage_symbolic.cu -- exact nnz(C_i) per row, binned by the upper bound p.
+//
+// k_sym_group<G,LOG2T> : a group of G lanes (8 or 32) owns a row and a T-slot column
+//                        table in shared memory; B rows are streamed one per step with
+//                        coalesced loads of their column segments.
+// k_sym_block<LOG2T>   : one CTA per row, up to 32768 slots (128 KB) -- the sizes for which
+//                        the reference needs its iterative merge with host re-allocation
+//                        (EM_mergepath, bhsparse_cuda.h:1902-2157, host loop :2527-2780).
+// k_sym_large          : rows beyond that: column bitmap in global memory (L2 resident).
+// None of these has a reference counterpart as a separate pass: the reference finds
+// nnz(C_i) as a by-product of its numeric kernels and compacts afterwards
+// (copyCt2C, :2813-2911); counting first lets C be allocated exactly and written once.
+#include "common.cuh"
+
+namespace bhb {
+
+template <int G, int LOG2T>
+__global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue, const int count,
+                                                   const int *__restrict__ rowptrA, const int *__restrict__ colA,
+                                                   const int *__restrict__ rowptrB, const int *__restrict__ colB,
+                                                   int *__restrict__ rc)
+{
+    constexpr int T = 1 << LOG2T;
+    extern __shared__ int smem_i[];
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x & (G - 1);
+    const int gib = threadIdx.x / G;
+    const int groups_per_block = blockDim.x / G;
+    const unsigned gmask = group_mask<G>(lane);
+    int *keys = smem_i + gib * T;
+
+    for (int q = blockIdx.x * groups_per_block + gib; q < count; q += gridDim.x * groups_per_block) {
+        const int row = queue[q];
+#pragma unroll 4
+        for (int s = gl; s < T; s += G) keys[s] = EMPTY_KEY;
+        __syncwarp(gmask);
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        int newcnt = 0;
+        for (int base = a0; base < a1; base += G) {
+            const int j = base + gl;
+            int bs = 0, be = 0;
+            if (j < a1) {
+                const int k = colA[j];
+                bs = rowptrB[k];
+                be = rowptrB[k + 1];
+            }
+            const int cnt = min(G, a1 - base);
+            for (int t = 0; t < cnt; ++t) {
+                const int s_bs = __shfl_sync(gmask, bs, t, G);
+                const int s_be = __shfl_sync(gmask, be, t, G);
+                for (int p = s_bs + gl; p < s_be; p += G) {
+                    bool is_new;
+                    table_insert<LOG2T>(keys, colB[p], is_new);
+                    newcnt += is_new;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = G >> 1; d > 0; d >>= 1) newcnt += __shfl_xor_sync(gmask, newcnt, d, G);
+        if (gl == 0) rc[row] = newcnt;
+        __syncwarp(gmask);
+    }
+}
+
+template <int LOG2T>
+__global__ void __launch_bounds__(512) k_sym_block(const int *__restrict__ queue, const int count,
+                                                   const int *__restrict__ rowptrA, const int *__restrict__ colA,
+                                                   const int *__restrict__ rowptrB, const int *__restrict__ colB,
+                                                   int *__restrict__ rc)
+{
+    constexpr int T = 1 << LOG2T;
+    extern __shared__ int smem_i[];
+    __shared__ int s_red[33];
+    int *keys = smem_i;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int row = queue[q];
+        for (int s = threadIdx.x; s < T; s += blockDim.x) keys[s] = EMPTY_KEY;
+        __syncthreads();
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        int newcnt = 0;
+        for (int j = a0 + warp; j < a1; j += nwarps) {
+            const int k = colA[j];
+            const int bs = rowptrB[k], be = rowptrB[k + 1];
+            for (int p = bs + lane; p < be; p += 32) {
+                bool is_new;
+                table_insert<LOG2T>(keys, colB[p], is_new);
+                newcnt += is_new;
+            }
+        }
+        const int tot = block_sum(newcnt, s_red);
+        if (threadIdx.x == 0) rc[row] = tot;
+        __syncthreads();
+    }
+}
+
+// Rows whose upper bound exceeds the largest shared-memory table.  Each resident CTA
+// owns an all-zero bitmap of n bits in global memory (it stays in the 126 MB L2); set
+// bits with atomicOr, count and clear the touched word range.
+__global__ void __launch_bounds__(1024) k_sym_large(const int *__restrict__ queue, const int count,
+                                                    const int *__restrict__ rowptrA, const int *__restrict__ colA,
+                                                    const int *__restrict__ rowptrB, const int *__restrict__ colB,
+                                                    int *__restrict__ rc, unsigned *__restrict__ bitmap_all,
+                                                    const int nwords)
+{
+    __shared__ int s_red[33];
+    __shared__ int s_lo, s_hi;
+    unsigned *bm = bitmap_all + (size_t)blockIdx.x * nwords;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int row = queue[q];
+        if (threadIdx.x == 0) {
+            s_lo = 0x7fffffff;
+            s_hi = -1;
+        }
+        __syncthreads();
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        int wlo = 0x7fffffff, whi = -1;
+        for (int j = a0 + warp; j < a1; j += nwarps) {
+            const int k = colA[j];
+            const int bs = rowptrB[k], be = rowptrB[k + 1];
+            for (int p = bs + lane; p < be; p += 32) {
+                const int c = colB[p];
+                const int w = c >> 5;
+                atomicOr(&bm[w], 1u << (c & 31));
+                wlo = min(wlo, w);
+                whi = max(whi, w);
+            }
+        }
+        if (whi >= 0) {
+            atomicMin(&s_lo, wlo);
+            atomicMax(&s_hi, whi);
+        }
+        __threadfence();
+        __syncthreads();
+        const int lo = s_lo, hi = s_hi;
+        int cnt = 0;
+        for (int w = lo + (int)threadIdx.x; w <= hi; w += blockDim.x) {
+            const unsigned bits = __ldcg(bm + w);
+            if (bits) {
+                cnt += __popc(bits);
+                bm[w] = 0u;
+            }
+        }
+        const int tot = block_sum(cnt, s_red);
+        if (threadIdx.x == 0) rc[row] = tot;
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+// ---- launchers -------------------------------------------------------------
+template <int G, int LOG2T>
+static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, int *rc)
+{
+    constexpr int T = 1 << LOG2T;
+    constexpr size_t per_group = (size_t)T * 4;
+    // groups per block: as many as fit ~64 KB, at most 256 threads, at least one warp
+    int groups = (int)((64 * 1024) / per_group);
+    const int max_groups = 256 / G;
+    if (groups > max_groups) groups = max_groups;
+    const int min_groups = 32 / G;
+    if (groups < min_groups) groups = min_groups;
+    const int threads = groups * G;
+    const size_t smem = per_group * groups;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_sym_group<G, LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    long long blocks = ((long long)count + groups - 1) / groups;
+    int per_sm = (int)((200 * 1024) / (smem ? smem : 1));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    const long long cap = (long long)lc.sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    ++*lc.launches;
+    k_sym_group<G, LOG2T><<<(int)blocks, threads, smem, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc);
+    return cudaGetLastError();
+}
+
+template <int LOG2T>
+static cudaError_t launch_sym_block_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, int *rc)
+{
+    constexpr int T = 1 << LOG2T;
+    const size_t smem = (size_t)T * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_sym_block<LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    int per_sm = (int)((200 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    long long blocks = count;
+    const long long cap = (long long)lc.sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    ++*lc.launches;
+    k_sym_block<LOG2T><<<(int)blocks, 512, smem, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B, int *rc)
+{
+    if (count <= 0) return cudaSuccess;
+#define SYM_GROUP_CASE(BIN, L2T)                                                                   \
+    case BIN:                                                                                      \
+        return (G == 8 && L2T <= 10) ? launch_sym_group_t<8, L2T>(lc, queue, count, A, B, rc)      \
+                                     : launch_sym_group_t<32, L2T>(lc, queue, count, A, B, rc);
+    switch (bin) {
+        SYM_GROUP_CASE(SB_G128, 7)
+        SYM_GROUP_CASE(SB_G256, 8)
+        SYM_GROUP_CASE(SB_G512, 9)
+        SYM_GROUP_CASE(SB_G1024, 10)
+        SYM_GROUP_CASE(SB_G2048, 11)
+        SYM_GROUP_CASE(SB_G4096, 12)
+    case SB_B8192: return launch_sym_block_t<13>(lc, queue, count, A, B, rc);
+    case SB_B16384: return launch_sym_block_t<14>(lc, queue, count, A, B, rc);
+    case SB_B32768: return launch_sym_block_t<15>(lc, queue, count, A, B, rc);
+    default: return cudaErrorInvalidValue;
+    }
+#undef SYM_GROUP_CASE
+}
+
+int large_scratch_blocks(int sm_count)
+{
+    return sm_count * 2;
+}
+
+cudaError_t launch_sym_large(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B, int *rc,
+                             unsigned *bitmap_scratch, int scratch_blocks)
+{
+    if (count <= 0) return cudaSuccess;
+    const int nwords = (n + 31) / 32;
+    int blocks = count < scratch_blocks ? count : scratch_blocks;
+    ++*lc.launches;
+    k_sym_large<<<blocks, 1024, 0, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc, bitmap_scratch, nwords);
+    return cudaGetLastError();
+}
+
+}  // namespace bhb

@@ -1,0 +1,148 @@
+/*
+ * bhsparse_b200.h -- C-ABI of the B200-native CSR SpGEMM (C = A*B) library.
+ *
+ * This is the drop-in boundary for the hot path of
+ * weifengliu-ssslab/Benchmark_SpGEMM_using_CSR: everything behind the public
+ * methods of class `bhsparse` (SpGEMM_cuda/bhsparse.h:17-34) and its CUDA
+ * back-end `bhsparse_cuda` (SpGEMM_cuda/bhsparse_cuda.h:17-90).  Plain C types
+ * only; no STL, torch, Thrust, CUB, cuSPARSE or CUSP types cross it.  The
+ * header-only C++ forwarder include/bhsparse.h rebuilds the reference class on
+ * top of these entry points; Python binds them with ctypes.
+ *
+ * CSR layout (bhsparse.h:22-25, common.h:30-31): int32 row pointers and column
+ * indices, 0-based; float or double values.  Rows of B must be sorted by column
+ * and duplicate-free (the reference's merge kernels assume the same,
+ * bhsparse_cuda.h:1730,1762).  Argument order is val, rowptr, colidx, as in the
+ * reference.
+ *
+ * Every function returns BHB200_SUCCESS (0 == BHSPARSE_SUCCESS, common.h:26) or
+ * a negative error code; nothing calls exit().  Not thread-safe per context
+ * (the reference is not either, bhsparse_cuda.h:100-101); distinct contexts may
+ * be used from distinct threads.
+ */
+#ifndef BHSPARSE_B200_H
+#define BHSPARSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BHB200_API __attribute__((visibility("default")))
+#else
+#define BHB200_API
+#endif
+
+#define BHB200_SUCCESS 0
+#define BHB200_ERR_INVALID (-1)      /* bad argument / call order                      */
+#define BHB200_ERR_CUDA (-2)         /* CUDA runtime error (see bhb200_last_error)     */
+#define BHB200_ERR_OVERFLOW (-3)     /* nnz(C) or a row does not fit the int32 API     */
+#define BHB200_ERR_ALLOC (-4)        /* device or host allocation failed               */
+#define BHB200_ERR_NO_DEVICE (-5)    /* no sm_100 device / device index out of range   */
+
+#define BHB200_DTYPE_F32 0
+#define BHB200_DTYPE_F64 1
+
+#define BHB200_NUM_SYM_BINS 16
+#define BHB200_NUM_NUM_BINS 16
+
+typedef struct bhb200_ctx bhb200_ctx;
+
+/* Per-call statistics of the last bhb200_spgemm (replaces the reference's
+ * stdout chatter: stage times bhsparse.h:307-336, "allocated size ... out of
+ * full size ..." :432, GFLOPS :286-289). */
+typedef struct bhb200_stats {
+    int64_t m, k, n, nnzA, nnzB;
+    int64_t products;        /* sum over rows of intermediate products = _nnzCt_full (bhsparse.h:368-406) */
+    int64_t nnzC;
+    int64_t max_row_products;
+    int64_t sym_bin_rows[BHB200_NUM_SYM_BINS]; /* rows per symbolic bin (by upper bound)       */
+    int64_t num_bin_rows[BHB200_NUM_NUM_BINS]; /* rows per numeric bin (by exact nnz(C_i))     */
+    float ms_total;          /* device time of the whole call (CUDA events)                    */
+    float ms_count;          /* stage 1: per-row upper bound + binning                         */
+    float ms_symbolic;       /* stage 2: per-bin symbolic kernels                              */
+    float ms_scan;           /* stage 3: row-pointer scan + numeric binning + C allocation     */
+    float ms_numeric;        /* stage 4: per-bin numeric kernels                               */
+    int32_t kernel_launches; /* kernels launched by the last call                              */
+    int32_t dtype;           /* BHB200_DTYPE_*                                                 */
+    int64_t bytes_algorithmic; /* stream-gather model, SURVEY.md 8(d)                          */
+    int64_t bytes_compulsory;  /* bytes(A)+bytes(B)+bytes(C)                                   */
+    int64_t workspace_bytes;   /* device memory currently held by the context                  */
+} bhb200_stats;
+
+/* -- platform --------------------------------------------------------------
+ * bhb200_create replaces bhsparse::initPlatform (bhsparse.h:96-124) and
+ * bhsparse_cuda::initPlatform (bhsparse_cuda.h:96-113, which hard-wires device
+ * 0).  bhb200_destroy replaces freePlatform (bhsparse.h:126-148). */
+BHB200_API int bhb200_create(bhb200_ctx **ctx, int device);
+BHB200_API int bhb200_destroy(bhb200_ctx *ctx);
+/* Run all work of this context on the caller's cudaStream_t (0 = the context's
+ * own non-blocking stream).  No reference counterpart (default stream only). */
+BHB200_API int bhb200_set_stream(bhb200_ctx *ctx, void *cuda_stream);
+BHB200_API const char *bhb200_last_error(const bhb200_ctx *ctx);
+BHB200_API const char *bhb200_device_name(const bhb200_ctx *ctx);
+BHB200_API int bhb200_sm_count(const bhb200_ctx *ctx);
+
+/* -- operands ----------------------------------------------------------------
+ * bhb200_init_data_{f64,f32} replace bhsparse::initData (bhsparse.h:180-258)
+ * -> bhsparse_cuda::initData (bhsparse_cuda.h:151-203): HOST pointers, copied
+ * to the device before the call returns; the caller keeps ownership.  A is
+ * m x k, B is k x n.  f64/f32 replaces the compile-time value_type typedef
+ * (common.h:31). */
+BHB200_API int bhb200_init_data_f64(bhb200_ctx *ctx, int m, int k, int n,
+                                    int nnzA, const double *valA, const int32_t *rowptrA, const int32_t *colA,
+                                    int nnzB, const double *valB, const int32_t *rowptrB, const int32_t *colB);
+BHB200_API int bhb200_init_data_f32(bhb200_ctx *ctx, int m, int k, int n,
+                                    int nnzA, const float *valA, const int32_t *rowptrA, const int32_t *colA,
+                                    int nnzB, const float *valB, const int32_t *rowptrB, const int32_t *colB);
+/* Same, but the six arrays are DEVICE pointers on the context's device and are
+ * borrowed (not copied, not freed) until bhb200_free_mem: the device-resident
+ * operand API of SURVEY.md 8(f).3, used by the multi-GPU row-block driver. */
+BHB200_API int bhb200_init_data_device(bhb200_ctx *ctx, int dtype, int m, int k, int n,
+                                       int nnzA, const void *valA, const int32_t *rowptrA, const int32_t *colA,
+                                       int nnzB, const void *valB, const int32_t *rowptrB, const int32_t *colB);
+
+/* -- the hot path --------------------------------------------------------------
+ * bhb200_warmup replaces bhsparse::warmup (bhsparse.h:341-363): runs the
+ * per-row upper-bound kernel once without touching any result.
+ * bhb200_spgemm replaces bhsparse::spgemm (bhsparse.h:260-339): all four stages
+ * on the device.  Unlike the reference it may be called repeatedly.  It returns
+ * after the last kernel has been enqueued and the sizes are known; results are
+ * complete after bhb200_synchronize or any bhb200_get_* call. */
+BHB200_API int bhb200_warmup(bhb200_ctx *ctx);
+BHB200_API int bhb200_spgemm(bhb200_ctx *ctx);
+BHB200_API int bhb200_synchronize(bhb200_ctx *ctx);
+
+/* -- results -------------------------------------------------------------------
+ * bhb200_get_nnzC replaces bhsparse::get_nnzC (bhsparse_cuda.h:3006-3009) with
+ * a 64-bit count.  bhb200_get_C_{f64,f32} replace bhsparse::get_C
+ * (bhsparse_cuda.h:3011-3020): device->host copy of rowptrC (m+1), colC and valC
+ * (nnzC each) into caller-allocated HOST arrays; any pointer may be NULL to skip
+ * it.  Returns BHB200_ERR_OVERFLOW if nnz(C) > INT32_MAX (use the _i64 row
+ * pointer variant then). */
+BHB200_API int64_t bhb200_get_nnzC(const bhb200_ctx *ctx);
+BHB200_API int bhb200_get_C_f64(bhb200_ctx *ctx, int32_t *rowptrC, int32_t *colC, double *valC);
+BHB200_API int bhb200_get_C_f32(bhb200_ctx *ctx, int32_t *rowptrC, int32_t *colC, float *valC);
+BHB200_API int bhb200_get_rowptrC_i64(bhb200_ctx *ctx, int64_t *rowptrC64);
+/* Device-resident result (borrowed until the next spgemm / free_mem):
+ * rowptr32 is NULL-valued when nnz(C) > INT32_MAX. */
+BHB200_API int bhb200_get_C_device(bhb200_ctx *ctx, const int32_t **rowptr32, const int64_t **rowptr64,
+                                   const int32_t **colC, const void **valC);
+/* Host copies of the per-row intermediate-product counts (int32[m], the
+ * reference's csrRowPtrCt contents, bhsparse_cuda.h:210-237) -- test hook. */
+BHB200_API int bhb200_get_row_products(bhb200_ctx *ctx, int32_t *row_products);
+BHB200_API int bhb200_get_stats(const bhb200_ctx *ctx, bhb200_stats *out);
+
+/* bhb200_free_mem replaces bhsparse::free_mem (bhsparse.h:150-177,
+ * bhsparse_cuda.h:121-149): releases operands, results and workspace. */
+BHB200_API int bhb200_free_mem(bhb200_ctx *ctx);
+
+/* Library identification: "bhsparse_b200 <version> sm_100a". */
+BHB200_API const char *bhb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHSPARSE_B200_H */
