@@ -1,0 +1,227 @@
+"""Parity of the CUDA path (through the C-ABI / the bhsparse class mirror) against
+the CPU oracle on the same seeded inputs.  rowptrC and colC bit-exact; values
+bit-exact for the integer-valued inputs the reference driver uses (main.cu:82,93),
+<= 1e-12 relative (double) / 1e-5 (float) for real-valued inputs -- the tolerances
+BASELINE.json's north_star states (the reference itself only checks 10 %,
+ref_spgemm.h:110)."""
+import numpy as np
+import pytest
+
+import oracle
+from benchmark_spgemm_using_csr_b200 import (BHSPARSE_CUDA, BHSPARSE_SUCCESS, NUM_PLATFORMS, bhsparse, capi,
+                                             generators as gen, spgemm)
+from benchmark_spgemm_using_csr_b200.generators import CSR
+from conftest import assert_csr_equal
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+def _oracle(A, B):
+    return oracle.spgemm(A.rows, A.cols, B.cols, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val)
+
+
+def _check(A, B, what, exact=True):
+    got = spgemm(A, B, return_stats=True)
+    st = got[3]
+    want = _oracle(A, B)
+    dt = A.val.dtype.type
+    assert_csr_equal(got[:3], want, exact_values=exact, rtol=RTOL[dt], what=what)
+    prod, total = oracle.row_products(A.rows, A.rowptr, A.col, B.rowptr)
+    assert st["products"] == total and st["nnzC"] == want[0][-1]
+    return st
+
+
+# ---- the reference's own cases ------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_kat_small_reference_call_sequence(golden, dt):
+    """test_small_spgemm (main.cu:149-246), call by call (main.cu:203-229)."""
+    g = golden("kat_small")
+    m, k, n = int(g["m"]), int(g["k"]), int(g["n"])
+    platforms = [False] * NUM_PLATFORMS
+    platforms[BHSPARSE_CUDA] = True
+    csrRowPtrC = np.zeros(m + 1, dtype=np.int32)
+    bh = bhsparse()
+    assert bh.initPlatform(platforms) == BHSPARSE_SUCCESS
+    assert bh.initData(m, k, n, 6, g["valA"].astype(dt), g["rowptrA"], g["colA"],
+                       7, g["valB"].astype(dt), g["rowptrB"], g["colB"], csrRowPtrC) == BHSPARSE_SUCCESS
+    assert bh.spgemm() == BHSPARSE_SUCCESS
+    nnzC = bh.get_nnzC()
+    assert nnzC == 6
+    csrColIndC = np.empty(nnzC, dtype=np.int32)
+    csrValC = np.empty(nnzC, dtype=dt)
+    assert bh.get_C(csrColIndC, csrValC) == BHSPARSE_SUCCESS
+    assert np.array_equal(bh.get_row_products(), g["products"])
+    assert bh.free_mem() == BHSPARSE_SUCCESS
+    assert bh.freePlatform() == BHSPARSE_SUCCESS
+    assert_csr_equal((csrRowPtrC, csrColIndC, csrValC), (g["rowptrC"], g["colC"], g["valC"].astype(dt)), what="kat")
+
+
+def test_cage4_squared(golden):
+    g = golden("cage4_sq")
+    m = int(g["m"])
+    A = CSR(m, m, g["rowptrA"], g["colA"], g["valA"])
+    got = spgemm(A, A)
+    assert_csr_equal(got, (g["rowptrC"], g["colC"], g["valC"]), exact_values=False, rtol=1e-12, what="cage4")
+
+
+@pytest.mark.parametrize("name,args,P,nnzC", [
+    ("poisson5pt", (256, 256), 1629192, 846852),         # -spgemm 1
+    ("poisson9pt", (256, 256), 5262436, 1623076),        # -spgemm 2
+    ("poisson7pt", (51, 51, 51), 6298245, 3207645),      # -spgemm 3
+    ("poisson27pt", (51, 51, 51), 90518849, 15438249),   # -spgemm 4
+])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_stock_workloads(name, args, P, nnzC, dt):
+    A = getattr(gen, name)(*args, dtype=dt)
+    st = _check(A, A, f"{name}{args} {dt.__name__}")
+    assert st["products"] == P and st["nnzC"] == nnzC
+
+
+# ---- every bin boundary ----------------------------------------------------------
+def _identity(n, dt):
+    return CSR(n, n, np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32), gen.int_values(n, 5, dt))
+
+
+P_EDGES = [0, 1, 2, 3, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 191, 192, 193, 255, 256, 257, 383, 384, 385,
+           511, 512, 513, 767, 768, 769, 1023, 1024, 1025, 1535, 1536, 1537, 2047, 2048, 2049, 3071, 3072, 3073,
+           4095, 4096, 4097, 6143, 6144, 6145, 8191, 8192, 8193, 12287, 12288, 12289, 24575, 24576, 24577, 40000]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_bin_boundaries_no_duplicates(dt):
+    """B = scaled identity: nnz(C_i) = products(i) = nnz(A_i), so one matrix walks
+    both the symbolic (by upper bound) and numeric (by nnz(C_i)) bin edges."""
+    n = 50000
+    sizes = np.array(P_EDGES * 2, dtype=np.int64)
+    A = gen.random_csr(sizes.size, n, sizes, seed=7, dtype=dt)
+    st = _check(A, _identity(n, dt), f"bin edges identity {dt.__name__}")
+    assert st["sym_bin_rows"][12] > 0 and st["num_bin_rows"][12] > 0      # the large bins ran
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("brow,ncols", [(5, 3000), (27, 2000), (64, 30000)])
+def test_bin_boundaries_with_duplicates(dt, brow, ncols):
+    """B rows of `brow` entries over few columns: heavy duplicate merging,
+    nnz(C_i) well below the upper bound, so symbolic and numeric bins differ."""
+    k = 4000
+    sizes = np.array([0, 1, 2, 3, 6, 7, 12, 13, 19, 20, 38, 39, 60, 77, 120, 150, 240, 300, 480, 600, 900, 1200, 2000,
+                      3000, 3999] * 2, dtype=np.int64)
+    A = gen.random_csr(sizes.size, k, sizes, seed=11, dtype=dt)
+    B = gen.random_csr(k, ncols, brow, seed=12, value_seed=13, dtype=dt)
+    _check(A, B, f"dup edges brow={brow} {dt.__name__}")
+
+
+def test_short_b_rows_select_narrow_groups():
+    """average referenced B row <= 10 -> 8-lane groups (config 4's shape, scaled down)."""
+    A = gen.uniform_rect(20000, 3000, per_row=8, seed=1, dtype=np.float32)
+    B = gen.uniform_rect(3000, 20000, per_row=8, seed=2, value_seed=3, dtype=np.float32)
+    st = _check(A, B, "uniform rect 8/row f32")
+    assert st["products"] == 20000 * 64
+    A2 = gen.random_csr(3000, 2500, (np.arange(3000) * 13) % 400, seed=5, dtype=np.float64)
+    B2 = gen.random_csr(2500, 6000, (np.arange(2500) * 7) % 9, seed=6, value_seed=8, dtype=np.float64)
+    _check(A2, B2, "short B rows, long A rows f64")
+
+
+def test_many_empty_b_rows_in_a_small_row():
+    """A row with > 32 entries whose products still fit one warp (ESC chunk loop)."""
+    k, n = 500, 400
+    lens = np.zeros(k, dtype=np.int64)
+    lens[::40] = 2
+    B = gen.random_csr(k, n, lens, seed=3)
+    A = gen.random_csr(64, k, 300, seed=4)
+    _check(A, B, "sparse B rows")
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_rmat_skewed(dt):
+    """Graph500-style skew: long rows -> block-hash and global-bitmap bins."""
+    A = gen.rmat(13, 16, a=0.57, b=0.19, c=0.19, d=0.05, seed=3, dtype=dt)
+    st = _check(A, A, f"rmat13 g500 {dt.__name__}")
+    assert sum(st["num_bin_rows"][9:13]) > 0
+    A = gen.rmat(14, 8, seed=4, dtype=dt)
+    _check(A, A, f"rmat14 mild {dt.__name__}")
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_real_values_within_tolerance(dt):
+    A = gen.poisson27pt(20, 20, 20, dtype=dt, values="real")
+    _check(A, A, "27pt real", exact=False)
+    A = gen.rmat(12, 16, a=0.57, b=0.19, c=0.19, d=0.05, seed=9, dtype=dt, values="real")
+    _check(A, A, "rmat real", exact=False)
+
+
+def test_explicit_zero_is_kept():
+    A = CSR(1, 2, np.array([0, 2], np.int32), np.array([0, 1], np.int32), np.array([1.0, -1.0]))
+    B = CSR(2, 1, np.array([0, 1, 2], np.int32), np.array([0, 0], np.int32), np.array([1.0, 1.0]))
+    rp, c, v = spgemm(A, B)
+    assert rp.tolist() == [0, 1] and c.tolist() == [0] and v.tolist() == [0.0]
+
+
+def test_empty_cases():
+    A = gen.random_csr(7, 5, [0, 2, 0, 1, 0, 0, 3], seed=1)
+    B = gen.random_csr(5, 9, 0, seed=2)
+    rp, c, v = spgemm(A, B)
+    assert rp.tolist() == [0] * 8 and c.size == 0
+    Z = gen.random_csr(6, 5, 0, seed=1)
+    B = gen.random_csr(5, 9, 3, seed=2)
+    rp, c, v = spgemm(Z, B)
+    assert rp.tolist() == [0] * 7 and c.size == 0
+    E = CSR(0, 5, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    rp, c, v = spgemm(E, B)
+    assert rp.tolist() == [0] and c.size == 0
+
+
+def test_wide_column_space():
+    """n > 2^26 switches the small-row kernel to 64-bit sort keys."""
+    n = (1 << 27) + 11
+    k = 64
+    rng = np.random.default_rng(5)
+    cols = np.sort(rng.integers(0, n - 3, size=(k, 3)), axis=1) + np.arange(3)[None, :]   # strictly ascending
+    cols[0] = [0, (1 << 27) - 1, n - 1]
+    cols = cols.astype(np.int32)
+    B = CSR(k, n, (np.arange(k + 1) * 3).astype(np.int32), cols.reshape(-1), gen.int_values(3 * k, 1))
+    A = gen.random_csr(200, k, (np.arange(200) % 11), seed=2)
+    _check(A, B, "wide columns")
+
+
+def test_repeated_calls_and_reinit():
+    """spgemm() twice on one initData (undefined in the reference, counters are
+    never reset: bhsparse.h:379-380) and re-initialisation on one context."""
+    platforms = [False] * NUM_PLATFORMS
+    platforms[BHSPARSE_CUDA] = True
+    bh = bhsparse()
+    assert bh.initPlatform(platforms) == 0
+    for dt, A in ((np.float64, gen.poisson9pt(64, 64)), (np.float32, gen.rmat(10, 8, dtype=np.float32))):
+        rowptrC = np.zeros(A.rows + 1, np.int32)
+        assert bh.initData(A.rows, A.cols, A.cols, A.nnz, A.val, A.rowptr, A.col,
+                           A.nnz, A.val, A.rowptr, A.col, rowptrC) == 0
+        want = _oracle(A, A)
+        for _ in range(3):
+            assert bh.warmup() == 0
+            assert bh.spgemm() == 0
+            colC = np.empty(bh.get_nnzC(), np.int32)
+            valC = np.empty(bh.get_nnzC(), dt)
+            assert bh.get_C(colC, valC) == 0
+            assert_csr_equal((rowptrC, colC, valC), want, what="repeat")
+            assert np.array_equal(bh.get_rowptrC_i64(), want[0])
+    assert bh.free_mem() == 0 and bh.freePlatform() == 0
+
+
+def test_error_paths():
+    bh = bhsparse()
+    assert bh.spgemm() != 0                              # before initPlatform
+    assert bh.initPlatform([False] * NUM_PLATFORMS) != 0   # no CUDA platform selected
+    platforms = [False] * NUM_PLATFORMS
+    platforms[BHSPARSE_CUDA] = True
+    assert bh.initPlatform(platforms) == 0
+    assert bh.spgemm() == capi.ERR_INVALID                # before initData
+    assert bh.get_nnzC() == -1
+    A = gen.poisson5pt(8, 8)
+    bad = A.rowptr.copy()
+    bad[-1] += 1
+    assert bh.initData(A.rows, A.cols, A.cols, A.nnz, A.val, bad, A.col, A.nnz, A.val, A.rowptr, A.col,
+                       np.zeros(A.rows + 1, np.int32)) == capi.ERR_INVALID
+    assert "rowptrA" in bh.last_error()
+    assert bh.freePlatform() == 0
