@@ -34,7 +34,7 @@ EXPORTED = [
     "bhb200_sm_count", "bhb200_init_data_f64", "bhb200_init_data_f32", "bhb200_init_data_device",
     "bhb200_warmup", "bhb200_spgemm", "bhb200_synchronize", "bhb200_get_nnzC", "bhb200_get_C_f64",
     "bhb200_get_C_f32", "bhb200_get_rowptrC_i64", "bhb200_get_C_device", "bhb200_get_row_products",
-    "bhb200_get_stats", "bhb200_free_mem", "bhb200_version",
+    "bhb200_get_stats", "bhb200_set_profiling", "bhb200_free_mem", "bhb200_version",
 ]
 
 
@@ -47,6 +47,9 @@ class Stats(ctypes.Structure):
         ("ms_numeric", c_float),
         ("kernel_launches", c_int32), ("dtype", c_int32),
         ("bytes_algorithmic", c_int64), ("bytes_compulsory", c_int64), ("workspace_bytes", c_int64),
+        ("num_bin_products", c_int64 * NUM_BINS), ("num_bin_nnzC", c_int64 * NUM_BINS),
+        ("num_bin_nnzA", c_int64 * NUM_BINS),
+        ("ms_sym_bin", c_float * NUM_BINS), ("ms_num_bin", c_float * NUM_BINS),
     ]
 
     def as_dict(self) -> dict:
@@ -107,6 +110,7 @@ def load(build_if_missing: bool = False):
     L.bhb200_get_C_device.argtypes = [ctxp, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     L.bhb200_get_row_products.argtypes = [ctxp, c_void_p]
     L.bhb200_get_stats.argtypes = [ctxp, POINTER(Stats)]
+    L.bhb200_set_profiling.argtypes = [ctxp, c_int]
     L.bhb200_free_mem.argtypes = [ctxp]
     for name in EXPORTED:
         f = getattr(L, name)

@@ -100,6 +100,9 @@ struct Counters {
     int num_bin[MAX_BINS];
     int sym_cursor[MAX_BINS];
     int num_cursor[MAX_BINS];
+    unsigned long long num_bin_products[MAX_BINS];
+    unsigned long long num_bin_nnzc[MAX_BINS];
+    unsigned long long num_bin_nnza[MAX_BINS];
 };
 struct BinOffsets {
     int off[MAX_BINS + 1];
@@ -277,8 +280,8 @@ struct LaunchCtx {
 cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, int *prod, int *rc, Counters *ctr);
 cudaError_t launch_bin_scatter(const LaunchCtx &lc, bool numeric, int m, const int *prod, const int *rc,
                                const BinOffsets &offs, Counters *ctr, int *queue);
-cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *prod, const int *rc, int64_t *rowoff64,
-                        int *rowptr32, long long *blocksums, Counters *ctr);
+cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *rowptrA, const int *prod, const int *rc,
+                        int64_t *rowoff64, int *rowptr32, long long *blocksums, Counters *ctr);
 size_t scan_blocksum_count(int m);
 // stage_small.cu
 cudaError_t launch_sym_esc(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B, int *rc);

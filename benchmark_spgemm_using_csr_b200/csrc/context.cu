@@ -84,6 +84,10 @@ struct bhb200_ctx {
     int64_t nnzC = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timing_valid = false;
+    bool profiling = false;
+    // per-launch events: [0] symbolic, [1] numeric; one before each bin + one after the last
+    cudaEvent_t ev_bin[2][MAX_BINS + 1] = {};
+    bool ev_bin_used[2][MAX_BINS + 1] = {};
     int launches = 0;
     bhb200_stats stats;
 };
@@ -218,6 +222,18 @@ int reserve_large_scratch(bhb200_ctx *ctx, bool need_prefix)
     return BHB200_SUCCESS;
 }
 
+// profiling: stamp the stream before bin `b` of phase `ph` (b == MAX_BINS: after the last bin)
+cudaError_t stamp(bhb200_ctx *ctx, int ph, int b)
+{
+    if (!ctx->profiling) return cudaSuccess;
+    if (!ctx->ev_bin[ph][b]) {
+        cudaError_t e = cudaEventCreate(&ctx->ev_bin[ph][b]);
+        if (e != cudaSuccess) return e;
+    }
+    ctx->ev_bin_used[ph][b] = true;
+    return cudaEventRecord(ctx->ev_bin[ph][b], ctx->stream);
+}
+
 void offsets_from_counts(const int *counts, BinOffsets &o)
 {
     int acc = 0;
@@ -304,6 +320,9 @@ int bhb200_destroy(bhb200_ctx *ctx)
     bhb200_free_mem(ctx);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &row : ctx->ev_bin)
+        for (auto &ev : row)
+            if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     cudaGetLastError();
@@ -431,27 +450,38 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(cudaEventRecord(ctx->ev[1], s), "event");
 
     // ---- stage 2: symbolic, one launch per non-empty bin ----
+    memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
+    if (hc.sym_bin[SB_ESC] > 0) CU(stamp(ctx, 0, SB_ESC), "event");
     CU(launch_sym_esc(lc, queue + so.off[SB_ESC], hc.sym_bin[SB_ESC], ctx->n, ctx->A, ctx->B, rcnt), "symbolic ESC");
-    for (int b = SB_G128; b <= SB_B32768; ++b)
+    for (int b = SB_G128; b <= SB_B32768; ++b) {
+        if (hc.sym_bin[b] > 0) CU(stamp(ctx, 0, b), "event");
         CU(launch_sym_hash(lc, b, G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, rcnt), "symbolic hash");
+    }
     if (hc.sym_bin[SB_LARGE] > 0) {
         rc = reserve_large_scratch(ctx, false);
         if (rc) return rc;
+        CU(stamp(ctx, 0, SB_LARGE), "event");
         CU(launch_sym_large(lc, queue + so.off[SB_LARGE], hc.sym_bin[SB_LARGE], ctx->n, ctx->A, ctx->B, rcnt,
                             ctx->bitmap.as<unsigned>(), large_scratch_blocks(ctx->sm_count)),
            "symbolic large");
     }
+    CU(stamp(ctx, 0, MAX_BINS), "event");
     CU(cudaEventRecord(ctx->ev[2], s), "event");
 
     // ---- stage 3: row pointers, numeric bins, exact allocation of C ----
-    CU(launch_scan(lc, ctx->m, prod, rcnt, rowoff, ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
+    CU(launch_scan(lc, ctx->m, ctx->A.rowptr, prod, rcnt, rowoff, ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
        "row pointer scan");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
     CU(cudaStreamSynchronize(s), "stage 2/3");
     hc = *ctx->h_ctr;
     ctx->nnzC = (int64_t)hc.nnzC;
     st.nnzC = ctx->nnzC;
-    for (int b = 0; b < BHB200_NUM_NUM_BINS && b < MAX_BINS; ++b) st.num_bin_rows[b] = hc.num_bin[b];
+    for (int b = 0; b < BHB200_NUM_NUM_BINS && b < MAX_BINS; ++b) {
+        st.num_bin_rows[b] = hc.num_bin[b];
+        st.num_bin_products[b] = (int64_t)hc.num_bin_products[b];
+        st.num_bin_nnzC[b] = (int64_t)hc.num_bin_nnzc[b];
+        st.num_bin_nnzA[b] = (int64_t)hc.num_bin_nnza[b];
+    }
     CU(ctx->colC.reserve((size_t)ctx->nnzC * 4 + 16, &ctx->dev_bytes), "alloc colC");
     CU(ctx->valC.reserve((size_t)ctx->nnzC * vs + 16, &ctx->dev_bytes), "alloc valC");
     BinOffsets no;
@@ -462,11 +492,14 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     // ---- stage 4: numeric, C written in place ----
     int *colC = ctx->colC.as<int>();
     void *valC = ctx->valC.p;
+    if (hc.num_bin[NB_ONE] > 0) CU(stamp(ctx, 1, NB_ONE), "event");
     CU(launch_num_single(lc, ctx->dtype, queue + no.off[NB_ONE], hc.num_bin[NB_ONE], ctx->A, ctx->B, rowoff, colC, valC),
        "numeric single");
+    if (hc.num_bin[NB_ESC] > 0) CU(stamp(ctx, 1, NB_ESC), "event");
     CU(launch_num_esc(lc, ctx->dtype, queue + no.off[NB_ESC], hc.num_bin[NB_ESC], ctx->n, ctx->A, ctx->B, rowoff, colC, valC),
        "numeric ESC");
     for (int b = NB_G64; b <= NB_B16384; ++b) {
+        if (hc.num_bin[b] > 0) CU(stamp(ctx, 1, b), "event");
         if (ctx->dtype == BHB200_DTYPE_F64)
             CU(launch_num_hash_f64(lc, b, G, queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rowoff, colC, (double *)valC),
                "numeric hash f64");
@@ -478,6 +511,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         rc = reserve_large_scratch(ctx, true);
         if (rc) return rc;
         const int sb = large_scratch_blocks(ctx->sm_count);
+        CU(stamp(ctx, 1, NB_LARGE), "event");
         if (ctx->dtype == BHB200_DTYPE_F64)
             CU(launch_num_large_f64(lc, queue + no.off[NB_LARGE], hc.num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
                                     (double *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
@@ -487,6 +521,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                                     (float *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
                "numeric large f32");
     }
+    CU(stamp(ctx, 1, MAX_BINS), "event");
     CU(cudaEventRecord(ctx->ev[4], s), "event");
 
     st.kernel_launches = ctx->launches;
@@ -499,6 +534,13 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     st.workspace_bytes = (int64_t)ctx->dev_bytes;
     ctx->have_C = true;
     ctx->timing_valid = true;
+    return BHB200_SUCCESS;
+}
+
+int bhb200_set_profiling(bhb200_ctx *ctx, int enabled)
+{
+    if (!ctx) return BHB200_ERR_INVALID;
+    ctx->profiling = enabled != 0;
     return BHB200_SUCCESS;
 }
 
@@ -586,6 +628,19 @@ int bhb200_get_stats(const bhb200_ctx *cctx, bhb200_stats *out)
         cudaEventElapsedTime(&st.ms_symbolic, ctx->ev[1], ctx->ev[2]);
         cudaEventElapsedTime(&st.ms_scan, ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&st.ms_numeric, ctx->ev[3], ctx->ev[4]);
+        if (ctx->profiling) {
+            // time of bin b = next stamped event - its own (launches are serial on one stream)
+            for (int ph = 0; ph < 2; ++ph) {
+                float *dst = ph ? st.ms_num_bin : st.ms_sym_bin;
+                for (int b = 0; b < MAX_BINS; ++b) {
+                    dst[b] = 0.f;
+                    if (!ctx->ev_bin_used[ph][b]) continue;
+                    int nx = b + 1;
+                    while (nx < MAX_BINS && !ctx->ev_bin_used[ph][nx]) ++nx;
+                    if (ctx->ev_bin_used[ph][nx]) cudaEventElapsedTime(&dst[b], ctx->ev_bin[ph][b], ctx->ev_bin[ph][nx]);
+                }
+            }
+        }
     }
     *out = ctx->stats;
     return BHB200_SUCCESS;

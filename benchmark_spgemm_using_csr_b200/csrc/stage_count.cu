@@ -176,14 +176,21 @@ size_t scan_blocksum_count(int m)
     return (size_t)((m + SCAN_CHUNK - 1) / SCAN_CHUNK) + 1;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int m, const int *__restrict__ prod,
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int m, const int *__restrict__ rowptrA,
+                                                              const int *__restrict__ prod,
                                                               const int *__restrict__ rc,
                                                               long long *__restrict__ blocksums,
                                                               Counters *__restrict__ ctr)
 {
     __shared__ int s_hist[MAX_BINS];
+    __shared__ unsigned long long s_work[3][MAX_BINS];   // products, nnz(C), nnz(A) per numeric bin
     __shared__ long long s_red[33];
-    if (threadIdx.x < MAX_BINS) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x < MAX_BINS) {
+        s_hist[threadIdx.x] = 0;
+        s_work[0][threadIdx.x] = 0ull;
+        s_work[1][threadIdx.x] = 0ull;
+        s_work[2][threadIdx.x] = 0ull;
+    }
     __syncthreads();
     const long long base = (long long)blockIdx.x * SCAN_CHUNK;
     long long s = 0;
@@ -192,13 +199,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int m, const
         const long long i = base + (long long)it * SCAN_THREADS + threadIdx.x;
         if (i < m) {
             const int c = rc[i];
+            const int p = prod[i];
             s += c;
-            atomicAdd(&s_hist[num_bin_of(prod[i], c)], 1);
+            const int b = num_bin_of(p, c);
+            atomicAdd(&s_hist[b], 1);
+            atomicAdd(&s_work[0][b], (unsigned long long)p);
+            atomicAdd(&s_work[1][b], (unsigned long long)c);
+            atomicAdd(&s_work[2][b], (unsigned long long)(rowptrA[i + 1] - rowptrA[i]));
         }
     }
     const long long tot = block_sum(s, s_red);
     if (threadIdx.x == 0) blocksums[blockIdx.x] = tot;
-    if (threadIdx.x < MAX_BINS && s_hist[threadIdx.x]) atomicAdd(&ctr->num_bin[threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x < MAX_BINS && s_hist[threadIdx.x]) {
+        atomicAdd(&ctr->num_bin[threadIdx.x], s_hist[threadIdx.x]);
+        atomicAdd(&ctr->num_bin_products[threadIdx.x], s_work[0][threadIdx.x]);
+        atomicAdd(&ctr->num_bin_nnzc[threadIdx.x], s_work[1][threadIdx.x]);
+        atomicAdd(&ctr->num_bin_nnza[threadIdx.x], s_work[2][threadIdx.x]);
+    }
 }
 
 // one block: exclusive scan of blocksums[0..nb) in place; total -> ctr->nnzC and blocksums[nb]
@@ -287,13 +304,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const int m, const 
     }
 }
 
-cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *prod, const int *rc, int64_t *rowoff64,
-                        int *rowptr32, long long *blocksums, Counters *ctr)
+cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *rowptrA, const int *prod, const int *rc,
+                        int64_t *rowoff64, int *rowptr32, long long *blocksums, Counters *ctr)
 {
     const int nb = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
     if (nb > 0) {
         ++*lc.launches;
-        k_scan_reduce<<<nb, SCAN_THREADS, 0, lc.stream>>>(m, prod, rc, blocksums, ctr);
+        k_scan_reduce<<<nb, SCAN_THREADS, 0, lc.stream>>>(m, rowptrA, prod, rc, blocksums, ctr);
     }
     ++*lc.launches;
     k_scan_blocks<<<1, 1024, 0, lc.stream>>>(nb, blocksums, ctr);

@@ -1,0 +1,270 @@
+"""1-D row-block SpGEMM across the GPUs of one node (one process per GPU).
+
+The reference is single-GPU (device 0 hard-wired, bhsparse_cuda.h:100-101); this
+is the multi-GPU scheme BASELINE.json's north_star asks for:
+
+  * rows of A are split into contiguous blocks whose boundaries sit on the prefix
+    sum of the per-row intermediate-product counts (NOT equal row counts: R-MAT
+    rows range from 0 to >10^5 products);
+  * B is broadcast once from the root with NCCL (three arrays: rowptr, col, val);
+  * every rank runs the single-GPU pipeline on its block (device-resident operands,
+    C-ABI bhb200_init_data_device / bhb200_spgemm);
+  * the per-rank nnz(C) are all-gathered (one int64 per rank) and exclusive-scanned
+    into each rank's global offset, so C is assembled without a host round trip:
+    global rowptrC of block r = local rowptrC + offset[r]; C stays row-sharded.
+
+There is no data-path collective inside the SpGEMM itself: C's row block depends
+only on A's row block and B.  torch.distributed is plumbing (NCCL on GPUs; gloo
+with CPU tensors in the host-logic tests, where the compute engine is injected).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi
+from .generators import CSR
+
+_NP2T = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+
+
+def row_products_host(A: CSR, B_rowptr: np.ndarray) -> np.ndarray:
+    """Per-row intermediate products on the host (partitioning only; the device
+    pipeline recomputes them in k_row_products)."""
+    lenB = np.diff(B_rowptr.astype(np.int64))
+    per_entry = lenB[A.col]
+    csum = np.zeros(A.nnz + 1, dtype=np.int64)
+    np.cumsum(per_entry, out=csum[1:])
+    return csum[A.rowptr[1:].astype(np.int64)] - csum[A.rowptr[:-1].astype(np.int64)]
+
+
+def partition_rows_by_products(row_products: np.ndarray, world: int) -> np.ndarray:
+    """Boundaries b[0..world] with b[0]=0, b[world]=m such that every block holds
+    about the same number of intermediate products (a row is never split)."""
+    m = int(row_products.size)
+    prefix = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(row_products, out=prefix[1:])
+    total = int(prefix[-1])
+    bounds = np.zeros(world + 1, dtype=np.int64)
+    bounds[world] = m
+    for r in range(1, world):
+        target = (total * r) // world
+        bounds[r] = int(np.searchsorted(prefix, target, side="left"))
+    bounds = np.maximum.accumulate(np.minimum(bounds, m))
+    return bounds
+
+
+@dataclass
+class LocalResult:
+    nnzC: int
+    rowptr64: object      # torch int64 [rows+1] (device) or numpy
+    col: object
+    val: object
+
+
+class CudaEngine:
+    """Runs one row block through the C-ABI with device-resident operands."""
+
+    def __init__(self, device: int):
+        self.lib = capi.load()
+        self.ctx = ctypes.c_void_p(None)
+        capi.check(self.lib, self.ctx, self.lib.bhb200_create(ctypes.byref(self.ctx), device))
+        self.device = device
+        self._keep = None
+
+    def use_stream(self, cuda_stream_ptr: int):
+        capi.check(self.lib, self.ctx, self.lib.bhb200_set_stream(self.ctx, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def set_operands(self, m, k, n, A, B):
+        """A, B = (rowptr, col, val) torch CUDA tensors (int32, int32, f32/f64)."""
+        self._keep = (A, B)
+        dtype = capi.DTYPE_F64 if A[2].dtype == torch.float64 else capi.DTYPE_F32
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        capi.check(self.lib, self.ctx, self.lib.bhb200_init_data_device(
+            self.ctx, dtype, m, k, n, int(A[1].numel()), p(A[2]), p(A[0]), p(A[1]),
+            int(B[1].numel()), p(B[2]), p(B[0]), p(B[1])))
+        self.m, self.vdtype = m, A[2].dtype
+
+    def spgemm(self) -> int:
+        capi.check(self.lib, self.ctx, self.lib.bhb200_spgemm(self.ctx))
+        return int(self.lib.bhb200_get_nnzC(self.ctx))
+
+    def result(self) -> LocalResult:
+        """Copies of the device-resident result as torch tensors (device to device)."""
+        nnzC = int(self.lib.bhb200_get_nnzC(self.ctx))
+        r32, r64, c, v = (ctypes.c_void_p() for _ in range(4))
+        capi.check(self.lib, self.ctx, self.lib.bhb200_get_C_device(
+            self.ctx, ctypes.byref(r32), ctypes.byref(r64), ctypes.byref(c), ctypes.byref(v)))
+        capi.check(self.lib, self.ctx, self.lib.bhb200_synchronize(self.ctx))
+        dev = torch.device("cuda", self.device)
+        rowptr = torch.empty(self.m + 1, dtype=torch.int64, device=dev)
+        col = torch.empty(nnzC, dtype=torch.int32, device=dev)
+        val = torch.empty(nnzC, dtype=self.vdtype, device=dev)
+        rt = torch.cuda.cudart()
+        for dst, src in ((rowptr, r64), (col, c), (val, v)):
+            if dst.numel():
+                err = rt.cudaMemcpy(dst.data_ptr(), src.value, dst.numel() * dst.element_size(), 3)  # D2D
+                if int(err) != 0:
+                    raise RuntimeError(f"cudaMemcpy D2D failed: {err}")
+        return LocalResult(nnzC, rowptr, col, val)
+
+    def stats(self) -> dict:
+        st = capi.Stats()
+        capi.check(self.lib, self.ctx, self.lib.bhb200_get_stats(self.ctx, ctypes.byref(st)))
+        return st.as_dict()
+
+    def set_profiling(self, on: bool):
+        self.lib.bhb200_set_profiling(self.ctx, 1 if on else 0)
+
+    def close(self):
+        if self.ctx:
+            self.lib.bhb200_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p(None)
+        self._keep = None
+
+
+class RowBlockSpGEMM:
+    """C = A*B with A row-partitioned over the ranks of `group` (see module doc)."""
+
+    def __init__(self, engine, device: torch.device, group=None):
+        self.engine = engine
+        self.device = device
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bounds = None
+        self.meta = None
+        self.A = None
+        self.B = None
+        self.timings = {}
+
+    # -- setup: partition, broadcast B, hand out the row blocks of A ---------------
+    def setup_from_root(self, A: CSR | None, B: CSR | None, root: int = 0, a_equals_b: bool = False):
+        """A, B are host CSR on `root` (None elsewhere).  With a_equals_b the row
+        blocks of A are sliced out of the broadcast copy of B instead of being sent."""
+        dev = self.device
+        if self.rank == root:
+            prods = row_products_host(A, B.rowptr)
+            bounds = partition_rows_by_products(prods, self.world)
+            meta = dict(m=A.rows, k=A.cols, n=B.cols, nnzA=A.nnz, nnzB=B.nnz, dtype=str(A.val.dtype),
+                        bounds=bounds.tolist(), nnz_bounds=[int(A.rowptr[b]) for b in bounds],
+                        products=int(prods.sum()))
+        else:
+            meta = None
+        if self.world > 1:
+            box = [meta]
+            dist.broadcast_object_list(box, src=root, group=self.group)
+            meta = box[0]
+        self.meta = meta
+        self.bounds = np.asarray(meta["bounds"], dtype=np.int64)
+        vt = _NP2T[np.dtype(meta["dtype"])]
+
+        # B: three broadcasts (rowptr first: it is all k_row_products needs)
+        def bcast(host_arr, numel, tdtype):
+            if self.rank == root:
+                t = torch.from_numpy(np.ascontiguousarray(host_arr)).to(dev, non_blocking=False)
+            else:
+                t = torch.empty(numel, dtype=tdtype, device=dev)
+            if self.world > 1:
+                dist.broadcast(t, src=root, group=self.group)
+            return t
+
+        t0 = _now(dev)
+        Brp = bcast(B.rowptr if B is not None else None, meta["k"] + 1, torch.int32)
+        Bc = bcast(B.col if B is not None else None, meta["nnzB"], torch.int32)
+        Bv = bcast(B.val if B is not None else None, meta["nnzB"], vt)
+        self.timings["broadcast_B_s"] = _now(dev) - t0
+        self.B = (Brp, Bc, Bv)
+
+        r0, r1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        e0, e1 = meta["nnz_bounds"][self.rank], meta["nnz_bounds"][self.rank + 1]
+        if a_equals_b:
+            Arp = (Brp[r0:r1 + 1] - Brp[r0]).contiguous()
+            self.A = (Arp, Bc[e0:e1], Bv[e0:e1])
+        else:
+            self.A = self._scatter_A(A, root, vt)
+        self.engine.set_operands(r1 - r0, meta["k"], meta["n"], self.A, self.B)
+        return self
+
+    def _scatter_A(self, A, root, vt):
+        dev = self.device
+        nb = self.meta["nnz_bounds"]
+        mine = None
+        if self.rank == root:
+            for r in range(self.world):
+                r0, r1 = int(self.bounds[r]), int(self.bounds[r + 1])
+                blk = (torch.from_numpy((A.rowptr[r0:r1 + 1] - A.rowptr[r0]).astype(np.int32)),
+                       torch.from_numpy(np.ascontiguousarray(A.col[nb[r]:nb[r + 1]])),
+                       torch.from_numpy(np.ascontiguousarray(A.val[nb[r]:nb[r + 1]])))
+                blk = tuple(t.to(dev) for t in blk)
+                if r == root:
+                    mine = blk
+                else:
+                    for t in blk:
+                        dist.send(t, dst=r, group=self.group)
+        else:
+            r0, r1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+            cnt = nb[self.rank + 1] - nb[self.rank]
+            mine = (torch.empty(r1 - r0 + 1, dtype=torch.int32, device=dev),
+                    torch.empty(cnt, dtype=torch.int32, device=dev), torch.empty(cnt, dtype=vt, device=dev))
+            for t in mine:
+                dist.recv(t, src=root, group=self.group)
+        return mine
+
+    # -- the step: local pipeline + one int64 all-gather ------------------------------
+    def spgemm(self):
+        """Returns (nnzC_local, global_offset, nnzC_total)."""
+        nnz_local = self.engine.spgemm()
+        if self.world > 1:
+            mine = torch.tensor([nnz_local], dtype=torch.int64, device=self.device)
+            parts = [torch.empty(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=self.group)
+            counts = torch.cat(parts).cpu().numpy()
+        else:
+            counts = np.array([nnz_local], dtype=np.int64)
+        offs = np.zeros(self.world + 1, dtype=np.int64)
+        np.cumsum(counts, out=offs[1:])
+        self.counts = counts
+        return nnz_local, int(offs[self.rank]), int(offs[-1])
+
+    # -- optional assembly: the full C on every rank (tests / small problems) ----------
+    def gather_full(self, offset: int, total: int):
+        """All-gather the row-sharded C into (rowptr int64[m+1], col, val) on every
+        rank.  Each rank contributes its block at its final offset; no host staging
+        of the payload."""
+        res = self.engine.result()
+        rowptr = _dev(res.rowptr64, self.device, torch.int64)
+        col = _dev(res.col, self.device, torch.int32)
+        val = _dev(res.val, self.device, None)
+        if self.world == 1:
+            return rowptr.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy()
+        m = self.meta["m"]
+        g_rowptr = torch.zeros(m + 1, dtype=torch.int64, device=self.device)
+        g_col = torch.zeros(total, dtype=torch.int32, device=self.device)
+        g_val = torch.zeros(total, dtype=val.dtype, device=self.device)
+        r0, r1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        g_rowptr[r0 + 1:r1 + 1] = rowptr[1:] + offset
+        g_col[offset:offset + res.nnzC] = col
+        g_val[offset:offset + res.nnzC] = val
+        # disjoint supports -> a sum all-reduce assembles the arrays in place
+        for t in (g_rowptr, g_col, g_val):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return g_rowptr.cpu().numpy(), g_col.cpu().numpy(), g_val.cpu().numpy()
+
+
+def _dev(x, device, dtype):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    x = x.to(device)
+    return x if dtype is None else x.to(dtype)
+
+
+def _now(device) -> float:
+    import time
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    return time.perf_counter()

@@ -70,6 +70,13 @@ typedef struct bhb200_stats {
     int64_t bytes_algorithmic; /* stream-gather model, SURVEY.md 8(d)                          */
     int64_t bytes_compulsory;  /* bytes(A)+bytes(B)+bytes(C)                                   */
     int64_t workspace_bytes;   /* device memory currently held by the context                  */
+    /* per numeric bin: work done by that bin's kernel (always filled) */
+    int64_t num_bin_products[BHB200_NUM_NUM_BINS];
+    int64_t num_bin_nnzC[BHB200_NUM_NUM_BINS];
+    int64_t num_bin_nnzA[BHB200_NUM_NUM_BINS];
+    /* per-bin kernel times in ms (CUDA events; only with bhb200_set_profiling(ctx, 1)) */
+    float ms_sym_bin[BHB200_NUM_SYM_BINS];
+    float ms_num_bin[BHB200_NUM_NUM_BINS];
 } bhb200_stats;
 
 /* -- platform --------------------------------------------------------------
@@ -134,6 +141,9 @@ BHB200_API int bhb200_get_C_device(bhb200_ctx *ctx, const int32_t **rowptr32, co
  * reference's csrRowPtrCt contents, bhsparse_cuda.h:210-237) -- test hook. */
 BHB200_API int bhb200_get_row_products(bhb200_ctx *ctx, int32_t *row_products);
 BHB200_API int bhb200_get_stats(const bhb200_ctx *ctx, bhb200_stats *out);
+/* Per-bin kernel timing (one CUDA event per launch; off by default).  Replaces the
+ * reference's dead `_profiling` switch (bhsparse_cuda.h:205-208, 728-733). */
+BHB200_API int bhb200_set_profiling(bhb200_ctx *ctx, int enabled);
 
 /* bhb200_free_mem replaces bhsparse::free_mem (bhsparse.h:150-177,
  * bhsparse_cuda.h:121-149): releases operands, results and workspace. */
