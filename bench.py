@@ -53,6 +53,9 @@ def make_workload(name: str, n_gpus: int, dtype):
         nz = 128 * n_gpus
         A = gen.poisson27pt(128, 128, nz, dtype=dtype)
         return A, A, True, f"Poisson27pt 3D 128x128x{nz} C=A^2"
+    if name == "poisson27thin":          # same stencil, narrow column span (48 x 48 planes)
+        A = gen.poisson27pt(48, 48, 1024 * n_gpus, dtype=dtype)
+        return A, A, True, f"Poisson27pt 3D 48x48x{1024 * n_gpus} C=A^2"
     if name == "poisson5":
         A = gen.poisson5pt(1024, 1024 * n_gpus, dtype=dtype)
         return A, A, True, f"Poisson5pt 2D 1024x{1024 * n_gpus} C=A^2"
@@ -156,7 +159,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="poisson27", choices=["poisson27", "poisson5", "rmat", "rect"])
+    ap.add_argument("--workload", default="poisson27", choices=["poisson27", "poisson27thin", "poisson5", "rmat", "rect"])
     ap.add_argument("--dtype", default=None, choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -225,8 +228,9 @@ def main():
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    bin_ms_sym = np.zeros(16)
-    bin_ms_num = np.zeros(16)
+    from benchmark_spgemm_using_csr_b200.capi import NUM_BINS
+    bin_ms_sym = np.zeros(NUM_BINS)
+    bin_ms_num = np.zeros(NUM_BINS)
     launches = 0
     barrier()
     ev0.record()
@@ -367,8 +371,8 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
         "stages_ms": {"count_bin": st["ms_count"], "symbolic": st["ms_symbolic"], "scan_alloc": st["ms_scan"],
                       "numeric": st["ms_numeric"], "total": st["ms_total"]},
-        "bins_ms": {"symbolic": {SYM_BIN_NAMES[i]: round(float(bin_ms_sym[i]), 4) for i in range(13) if bin_ms_sym[i] > 0},
-                    "numeric": {NUM_BIN_NAMES[i]: round(float(bin_ms_num[i]), 4) for i in range(13) if bin_ms_num[i] > 0}},
+        "bins_ms": {"symbolic": {SYM_BIN_NAMES[i]: round(float(bin_ms_sym[i]), 4) for i in range(len(SYM_BIN_NAMES)) if bin_ms_sym[i] > 0},
+                    "numeric": {NUM_BIN_NAMES[i]: round(float(bin_ms_num[i]), 4) for i in range(len(NUM_BIN_NAMES)) if bin_ms_num[i] > 0}},
         "setup_broadcast_ms": rb.timings.get("broadcast_B_s", 0.0) * 1e3,
     }
     print(json.dumps(line), flush=True)

@@ -25,10 +25,11 @@ SOURCES = [
     "stage_count.cu",
     "stage_small.cu",
     "stage_symbolic.cu",
+    "stage_range.cu",
     "stage_numeric_f32.cu",
     "stage_numeric_f64.cu",
 ]
-HEADERS = ["common.cuh", "stage_numeric.cuh", os.path.join(INCLUDE, "bhsparse_b200.h")]
+HEADERS = ["common.cuh", "stage_numeric.cuh", "stage_range.cuh", "stage_range_vec.cuh", os.path.join(INCLUDE, "bhsparse_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -21,12 +21,12 @@ ERR_ALLOC = -4
 ERR_NO_DEVICE = -5
 DTYPE_F32 = 0
 DTYPE_F64 = 1
-NUM_BINS = 16
+NUM_BINS = 24
 
 SYM_BIN_NAMES = ["p=0", "p=1", "esc<=32", "g128", "g256", "g512", "g1024", "g2048", "g4096",
-                 "b8192", "b16384", "b32768", "large"]
+                 "b8192", "b16384", "b32768", "large", "range_s", "range_l"]
 NUM_BIN_NAMES = ["c=0", "p=1", "esc<=32", "g64", "g128", "g256", "g512", "g1024", "g2048",
-                 "b4096", "b8192", "b16384", "large"]
+                 "b4096", "b8192", "b16384", "large", "range_s128", "range_s512", "range_l128", "range_l512"]
 
 # every symbol include/bhsparse_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = [

@@ -20,10 +20,22 @@ constexpr int SORT_PAD = 0x7fffffff;
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- bins ------------------------------------------------------------------
-// Symbolic bins are chosen by p = upper bound of the row (products); numeric
-// bins by c = exact nnz(C_i) (and p for the tiny rows).  They play the role of
-// the reference's 128 segments (bhsparse.h:373-407) but the boundaries follow
-// the B200's 227 KB shared memory instead of 32/64/128/256/512/2304.
+// Symbolic bins are chosen by p = upper bound of the row (products) and by the row's
+// column span; numeric bins by c = exact nnz(C_i), p and the span.  They play the role
+// of the reference's 128 segments (bhsparse.h:373-407) but the boundaries follow the
+// B200's 227 KB shared memory instead of 32/64/128/256/512/2304.
+//
+// "span" = (max column - min column + 1) any product of the row can have, from the
+// first/last column of every referenced B row.  Rows whose span fits a shared-memory
+// bitmap (stencil / banded / FEM rows) take the *range* kernels: a column's position in
+// the sorted output row is a popcount prefix of that bitmap, so there is no hashing,
+// no probing and no sort.  Everything else takes the hash kernels.
+constexpr int SPAN_SMALL = 12288 - 64;    // bitmap of 6 x 2048 columns   (1.5 KB)
+constexpr int SPAN_LARGE = 69632 - 64;    // bitmap of 34 x 2048 columns  (8.5 KB)
+constexpr int NSUM_SMALL = 6;             // summary words (one bit per 64-column word)
+constexpr int NSUM_LARGE = 34;
+constexpr int RANGE_NACC_MAX = 512;       // largest nnz(C_i) a range kernel accumulates
+
 enum SymBin {
     SB_ZERO = 0,   // p == 0            -> nnz(C_i) = 0, no kernel   (ESC_0, bhsparse_cuda.h:1582)
     SB_ONE = 1,    // p == 1            -> nnz(C_i) = 1, no kernel   (ESC_1, :1597)
@@ -38,7 +50,9 @@ enum SymBin {
     SB_B16384 = 10, // p <= 12288
     SB_B32768 = 11, // p <= 24576
     SB_LARGE = 12,  // beyond           -> global bitmap             (EM_mergepath_global, :2270)
-    SB_COUNT = 13
+    SB_RANGE_S = 13, // p > 32, span <= SPAN_SMALL -> shared-memory bitmap
+    SB_RANGE_L = 14, // p > 32, span <= SPAN_LARGE
+    SB_COUNT = 15
 };
 enum NumBin {
     NB_ZERO = 0,   // c == 0
@@ -54,14 +68,20 @@ enum NumBin {
     NB_B8192 = 10, // c <= 4096
     NB_B16384 = 11, // c <= 8192
     NB_LARGE = 12,  // beyond    global bitmap-rank accumulation
-    NB_COUNT = 13
+    NB_RANGE_S128 = 13, // span <= SPAN_SMALL, c <= 128  -> bitmap-rank in shared memory
+    NB_RANGE_S512 = 14, // span <= SPAN_SMALL, c <= 512
+    NB_RANGE_L128 = 15, // span <= SPAN_LARGE, c <= 128
+    NB_RANGE_L512 = 16, // span <= SPAN_LARGE, c <= 512
+    NB_COUNT = 17
 };
-constexpr int MAX_BINS = 16;
+constexpr int MAX_BINS = 24;
 
-__host__ __device__ __forceinline__ int sym_bin_of(int p)
+__host__ __device__ __forceinline__ int sym_bin_of(int p, int span)
 {
     if (p <= 1) return p;
     if (p <= 32) return SB_ESC;
+    if (span <= SPAN_SMALL) return SB_RANGE_S;
+    if (span <= SPAN_LARGE) return SB_RANGE_L;
     if (p <= 96) return SB_G128;
     if (p <= 192) return SB_G256;
     if (p <= 384) return SB_G512;
@@ -73,10 +93,14 @@ __host__ __device__ __forceinline__ int sym_bin_of(int p)
     if (p <= 24576) return SB_B32768;
     return SB_LARGE;
 }
-__host__ __device__ __forceinline__ int num_bin_of(int p, int c)
+__host__ __device__ __forceinline__ int num_bin_of(int p, int c, int span)
 {
     if (p <= 1) return p;
     if (p <= 32) return NB_ESC;
+    if (c <= RANGE_NACC_MAX) {
+        if (span <= SPAN_SMALL) return c <= 128 ? NB_RANGE_S128 : NB_RANGE_S512;
+        if (span <= SPAN_LARGE) return c <= 128 ? NB_RANGE_L128 : NB_RANGE_L512;
+    }
     if (c <= 32) return NB_G64;
     if (c <= 64) return NB_G128;
     if (c <= 128) return NB_G256;
@@ -94,6 +118,7 @@ __host__ __device__ __forceinline__ int num_bin_of(int p, int c)
 struct Counters {
     unsigned long long products;   // sum of per-row products (_nnzCt_full, bhsparse.h:368)
     unsigned long long nnzC;       // set by the scan
+    unsigned long long pool_cursor;  // word-list pool: entries handed out by the symbolic range kernel
     int max_row_products;
     int row_overflow;              // a row's product count did not fit int32
     int sym_bin[MAX_BINS];
@@ -106,6 +131,18 @@ struct Counters {
 };
 struct BinOffsets {
     int off[MAX_BINS + 1];
+};
+
+// Word lists: the symbolic range kernel stores, per row, the non-empty 64-column words of
+// the row's bitmap (index + bits) in a device pool; the numeric range kernel rebuilds its
+// bitmap and the rank prefixes from that list instead of walking all products a second
+// time.  wl_cnt[row] < 0: the pool was full, the numeric kernel marks the row itself.
+struct WordLists {
+    long long *off;                  // [m] first pool entry of the row
+    int *cnt;                        // [m] entries, or -1
+    unsigned *idx;                   // [cap] word index inside the row's bitmap
+    unsigned long long *bits;        // [cap]
+    long long cap;
 };
 
 // ---- hashing ---------------------------------------------------------------
@@ -274,14 +311,17 @@ struct LaunchCtx {
     cudaStream_t stream;
     int sm_count;
     int *launches;   // incremented per kernel launch
+    int max_span = SPAN_SMALL;   // rows with a wider column span never take the range kernels
 };
 
 // stage_count.cu
-cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, int *prod, int *rc, Counters *ctr);
+cudaError_t launch_b_row_ranges(const LaunchCtx &lc, int k, Csr B, int2 *brange);
+cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, const int2 *brange, int *prod,
+                                int *rc, int *rlo, int *rspan, Counters *ctr);
 cudaError_t launch_bin_scatter(const LaunchCtx &lc, bool numeric, int m, const int *prod, const int *rc,
-                               const BinOffsets &offs, Counters *ctr, int *queue);
+                               const int *rspan, const BinOffsets &offs, Counters *ctr, int *queue);
 cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *rowptrA, const int *prod, const int *rc,
-                        int64_t *rowoff64, int *rowptr32, long long *blocksums, Counters *ctr);
+                        const int *rspan, int64_t *rowoff64, int *rowptr32, long long *blocksums, Counters *ctr);
 size_t scan_blocksum_count(int m);
 // stage_small.cu
 cudaError_t launch_sym_esc(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B, int *rc);
@@ -305,5 +345,13 @@ cudaError_t launch_num_large_f64(const LaunchCtx &lc, const int *queue, int coun
                                  const int64_t *rowoff, int *colC, double *valC, unsigned *bitmap_scratch,
                                  int *prefix_scratch, int scratch_blocks);
 int large_scratch_blocks(int sm_count);
+// stage_range.cu (symbolic) / stage_numeric (numeric) -- shared-memory bitmap kernels
+// (the launchers pick the 128-bit vectorised kernels of stage_range_vec.cuh when B is 16-byte aligned)
+cudaError_t launch_sym_range(const LaunchCtx &lc, int nsum, const int *queue, int count, Csr A, Csr B, const int *rlo,
+                             int *rc, Counters *ctr, WordLists wl);
+cudaError_t launch_num_range_f32(const LaunchCtx &lc, int nsum, int nacc, const int *queue, int count, Csr A, Csr B,
+                                 const int *rlo, const int64_t *rowoff, int *colC, float *valC, WordLists wl);
+cudaError_t launch_num_range_f64(const LaunchCtx &lc, int nsum, int nacc, const int *queue, int count, Csr A, Csr B,
+                                 const int *rlo, const int64_t *rowoff, int *colC, double *valC, WordLists wl);
 
 }  // namespace bhb

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -75,6 +76,7 @@ struct bhb200_ctx {
 
     // workspace (grow-only, reused across calls)
     DevBuf prod, rc, queue, rowoff64, rowptr32, blocksums, counters, bitmap, prefix;
+    DevBuf brange, rlo, rspan, wl_off, wl_cnt, wl_idx, wl_bits;   // span info + word-list pool (range kernels)
     size_t bitmap_zeroed_bytes = 0;
     DevBuf colC, valC;
     Counters *h_ctr = nullptr;   // pinned
@@ -85,6 +87,7 @@ struct bhb200_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timing_valid = false;
     bool profiling = false;
+    int max_span = SPAN_SMALL;   // BHB200_RANGE=off|small|all overrides (experiments)
     // per-launch events: [0] symbolic, [1] numeric; one before each bin + one after the last
     cudaEvent_t ev_bin[2][MAX_BINS + 1] = {};
     bool ev_bin_used[2][MAX_BINS + 1] = {};
@@ -202,6 +205,9 @@ int reserve_workspace(bhb200_ctx *ctx)
     CU(ctx->rowptr32.reserve(m1 * 4, &ctx->dev_bytes), "alloc rowptrC");
     CU(ctx->blocksums.reserve((scan_blocksum_count(ctx->m) + 1) * 8, &ctx->dev_bytes), "alloc scan sums");
     CU(ctx->counters.reserve(sizeof(Counters), &ctx->dev_bytes), "alloc counters");
+    CU(ctx->brange.reserve(((size_t)ctx->k + 1) * 8, &ctx->dev_bytes), "alloc B row ranges");
+    CU(ctx->rlo.reserve(m1 * 4, &ctx->dev_bytes), "alloc row min column");
+    CU(ctx->rspan.reserve(m1 * 4, &ctx->dev_bytes), "alloc row span");
     return BHB200_SUCCESS;
 }
 
@@ -232,6 +238,33 @@ cudaError_t stamp(bhb200_ctx *ctx, int ph, int b)
     }
     ctx->ev_bin_used[ph][b] = true;
     return cudaEventRecord(ctx->ev_bin[ph][b], ctx->stream);
+}
+
+// word-list pool of the range kernels: sized from the product count of the call; if it is
+// too small (or cannot be allocated) the numeric kernel marks the affected rows itself
+int reserve_word_lists(bhb200_ctx *ctx, int64_t products, WordLists &wl)
+{
+    const size_t m1 = (size_t)ctx->m + 1;
+    CU(ctx->wl_off.reserve(m1 * 8, &ctx->dev_bytes), "alloc word-list offsets");
+    CU(ctx->wl_cnt.reserve(m1 * 4, &ctx->dev_bytes), "alloc word-list counts");
+    long long cap = products / 4 + (long long)ctx->m + 1024;
+    if (cap > (1ll << 31)) cap = 1ll << 31;
+    if (const char *dbg = getenv("BHB200_DEBUG_WORDLIST_CAP")) cap = atoll(dbg);   // tests: force the fallback
+    if (ctx->wl_idx.reserve((size_t)cap * 4, &ctx->dev_bytes) != cudaSuccess ||
+        ctx->wl_bits.reserve((size_t)cap * 8, &ctx->dev_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        cap = 0;   // no pool: every row falls back to marking in the numeric kernel
+    } else {
+        // grow-only buffers may be larger than this call's request: use all of it
+        const long long have = (long long)(ctx->wl_idx.cap / 4 < ctx->wl_bits.cap / 8 ? ctx->wl_idx.cap / 4 : ctx->wl_bits.cap / 8);
+        if (have > cap && !getenv("BHB200_DEBUG_WORDLIST_CAP")) cap = have;
+    }
+    wl.off = ctx->wl_off.as<long long>();
+    wl.cnt = ctx->wl_cnt.as<int>();
+    wl.idx = ctx->wl_idx.as<unsigned>();
+    wl.bits = ctx->wl_bits.as<unsigned long long>();
+    wl.cap = cap;
+    return BHB200_SUCCESS;
 }
 
 void offsets_from_counts(const int *counts, BinOffsets &o)
@@ -289,6 +322,11 @@ int bhb200_create(bhb200_ctx **out, int device)
         return BHB200_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *rm = getenv("BHB200_RANGE")) {
+        if (!strcmp(rm, "off")) ctx->max_span = -1;
+        else if (!strcmp(rm, "small")) ctx->max_span = SPAN_SMALL;
+        else if (!strcmp(rm, "all")) ctx->max_span = SPAN_LARGE;
+    }
     for (auto &ev : ctx->ev) {
         if (cudaEventCreate(&ev) != cudaSuccess) {
             cudaGetLastError();
@@ -306,7 +344,8 @@ int bhb200_free_mem(bhb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     release_operands(ctx);
-    DevBuf *bufs[] = {&ctx->prod, &ctx->rc, &ctx->queue, &ctx->rowoff64, &ctx->rowptr32, &ctx->blocksums,
+    DevBuf *bufs[] = {&ctx->brange, &ctx->rlo, &ctx->rspan, &ctx->wl_off, &ctx->wl_cnt, &ctx->wl_idx, &ctx->wl_bits,
+                      &ctx->prod, &ctx->rc, &ctx->queue, &ctx->rowoff64, &ctx->rowptr32, &ctx->blocksums,
                       &ctx->counters, &ctx->bitmap, &ctx->prefix, &ctx->colC, &ctx->valC};
     for (DevBuf *b : bufs) b->release(&ctx->dev_bytes);
     ctx->bitmap_zeroed_bytes = 0;
@@ -395,10 +434,11 @@ int bhb200_warmup(bhb200_ctx *ctx)
     if (ctx->m == 0) return BHB200_SUCCESS;
     int rc = reserve_workspace(ctx);
     if (rc) return rc;
-    LaunchCtx lc{ctx->stream, ctx->sm_count, &ctx->launches};
+    LaunchCtx lc{ctx->stream, ctx->sm_count, &ctx->launches, ctx->max_span};
     CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), ctx->stream), "zero counters");
-    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->prod.as<int>(), ctx->rc.as<int>(),
-                           ctx->counters.as<Counters>()),
+    CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int2>()), "B row ranges kernel");
+    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int2>(), ctx->prod.as<int>(),
+                           ctx->rc.as<int>(), ctx->rlo.as<int>(), ctx->rspan.as<int>(), ctx->counters.as<Counters>()),
        "row products kernel");
     ctx->have_C = false;
     return BHB200_SUCCESS;
@@ -423,7 +463,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     cudaStream_t s = ctx->stream;
     int rc = reserve_workspace(ctx);
     if (rc) return rc;
-    LaunchCtx lc{s, ctx->sm_count, &ctx->launches};
+    LaunchCtx lc{s, ctx->sm_count, &ctx->launches, ctx->max_span};
     Counters *d_ctr = ctx->counters.as<Counters>();
     int *prod = ctx->prod.as<int>();
     int *rcnt = ctx->rc.as<int>();
@@ -433,7 +473,11 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     // ---- stage 1: upper bound per row + symbolic bins ----
     CU(cudaEventRecord(ctx->ev[0], s), "event");
     CU(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s), "zero counters");
-    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, prod, rcnt, d_ctr), "row products kernel");
+    int *rlo = ctx->rlo.as<int>();
+    int *rspan = ctx->rspan.as<int>();
+    CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int2>()), "B row ranges kernel");
+    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int2>(), prod, rcnt, rlo, rspan, d_ctr),
+       "row products kernel");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
     CU(cudaStreamSynchronize(s), "stage 1");
     Counters hc = *ctx->h_ctr;
@@ -446,7 +490,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     const int G = avg_b <= 10.0 ? 8 : 32;
     BinOffsets so;
     offsets_from_counts(hc.sym_bin, so);
-    CU(launch_bin_scatter(lc, false, ctx->m, prod, rcnt, so, d_ctr, queue), "symbolic bin scatter");
+    CU(launch_bin_scatter(lc, false, ctx->m, prod, rcnt, rspan, so, d_ctr, queue), "symbolic bin scatter");
     CU(cudaEventRecord(ctx->ev[1], s), "event");
 
     // ---- stage 2: symbolic, one launch per non-empty bin ----
@@ -465,11 +509,28 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                             ctx->bitmap.as<unsigned>(), large_scratch_blocks(ctx->sm_count)),
            "symbolic large");
     }
+    WordLists wl{nullptr, nullptr, nullptr, nullptr, 0};
+    if (hc.sym_bin[SB_RANGE_S] + hc.sym_bin[SB_RANGE_L] > 0) {
+        rc = reserve_word_lists(ctx, st.products, wl);
+        if (rc) return rc;
+        if (hc.sym_bin[SB_RANGE_S] > 0) {
+            CU(stamp(ctx, 0, SB_RANGE_S), "event");
+            CU(launch_sym_range(lc, NSUM_SMALL, queue + so.off[SB_RANGE_S], hc.sym_bin[SB_RANGE_S], ctx->A, ctx->B, rlo,
+                                rcnt, d_ctr, wl),
+               "symbolic range (small span)");
+        }
+        if (hc.sym_bin[SB_RANGE_L] > 0) {
+            CU(stamp(ctx, 0, SB_RANGE_L), "event");
+            CU(launch_sym_range(lc, NSUM_LARGE, queue + so.off[SB_RANGE_L], hc.sym_bin[SB_RANGE_L], ctx->A, ctx->B, rlo,
+                                rcnt, d_ctr, wl),
+               "symbolic range (large span)");
+        }
+    }
     CU(stamp(ctx, 0, MAX_BINS), "event");
     CU(cudaEventRecord(ctx->ev[2], s), "event");
 
     // ---- stage 3: row pointers, numeric bins, exact allocation of C ----
-    CU(launch_scan(lc, ctx->m, ctx->A.rowptr, prod, rcnt, rowoff, ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
+    CU(launch_scan(lc, ctx->m, ctx->A.rowptr, prod, rcnt, rspan, rowoff, ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
        "row pointer scan");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
     CU(cudaStreamSynchronize(s), "stage 2/3");
@@ -486,7 +547,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(ctx->valC.reserve((size_t)ctx->nnzC * vs + 16, &ctx->dev_bytes), "alloc valC");
     BinOffsets no;
     offsets_from_counts(hc.num_bin, no);
-    CU(launch_bin_scatter(lc, true, ctx->m, prod, rcnt, no, d_ctr, queue), "numeric bin scatter");
+    CU(launch_bin_scatter(lc, true, ctx->m, prod, rcnt, rspan, no, d_ctr, queue), "numeric bin scatter");
     CU(cudaEventRecord(ctx->ev[3], s), "event");
 
     // ---- stage 4: numeric, C written in place ----
@@ -520,6 +581,24 @@ int bhb200_spgemm(bhb200_ctx *ctx)
             CU(launch_num_large_f32(lc, queue + no.off[NB_LARGE], hc.num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
                                     (float *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
                "numeric large f32");
+    }
+    {
+        const int rb[4] = {NB_RANGE_S128, NB_RANGE_S512, NB_RANGE_L128, NB_RANGE_L512};
+        const int rnsum[4] = {NSUM_SMALL, NSUM_SMALL, NSUM_LARGE, NSUM_LARGE};
+        const int rnacc[4] = {128, RANGE_NACC_MAX, 128, RANGE_NACC_MAX};
+        for (int i = 0; i < 4; ++i) {
+            const int b = rb[i];
+            if (hc.num_bin[b] <= 0) continue;
+            CU(stamp(ctx, 1, b), "event");
+            if (ctx->dtype == BHB200_DTYPE_F64)
+                CU(launch_num_range_f64(lc, rnsum[i], rnacc[i], queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rlo, rowoff,
+                                        colC, (double *)valC, wl),
+                   "numeric range f64");
+            else
+                CU(launch_num_range_f32(lc, rnsum[i], rnacc[i], queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rlo, rowoff,
+                                        colC, (float *)valC, wl),
+                   "numeric range f32");
+        }
     }
     CU(stamp(ctx, 1, MAX_BINS), "event");
     CU(cudaEventRecord(ctx->ev[4], s), "event");

@@ -13,11 +13,33 @@ namespace bhb {
 // gathers of a warp are issued together.  Also builds the symbolic-bin
 // histogram, the product total (int64) and settles rows with p <= 1.
 // ---------------------------------------------------------------------------
+// k_b_row_ranges: first and last column of every row of B ({INT_MAX,-1} for empty rows);
+// one 8-byte gather per A entry then bounds the column span of a row of C.
+__global__ void __launch_bounds__(256) k_b_row_ranges(const int k, const int *__restrict__ rowptrB,
+                                                      const int *__restrict__ colB, int2 *__restrict__ brange)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= k) return;
+    const int s = rowptrB[r], e = rowptrB[r + 1];
+    brange[r] = (e > s) ? make_int2(colB[s], colB[e - 1]) : make_int2(0x7fffffff, -1);
+}
+
+cudaError_t launch_b_row_ranges(const LaunchCtx &lc, int k, Csr B, int2 *brange)
+{
+    if (k <= 0) return cudaSuccess;
+    ++*lc.launches;
+    k_b_row_ranges<<<(k + 255) / 256, 256, 0, lc.stream>>>(k, B.rowptr, B.col, brange);
+    return cudaGetLastError();
+}
+
 template <int G>
 __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__restrict__ rowptrA,
                                                       const int *__restrict__ colA,
-                                                      const int *__restrict__ rowptrB, int *__restrict__ prod,
-                                                      int *__restrict__ rc, Counters *__restrict__ ctr)
+                                                      const int *__restrict__ rowptrB,
+                                                      const int2 *__restrict__ brange, int *__restrict__ prod,
+                                                      int *__restrict__ rc, int *__restrict__ rlo,
+                                                      int *__restrict__ rspan, const int max_span,
+                                                      Counters *__restrict__ ctr)
 {
     __shared__ int s_hist[MAX_BINS];
     __shared__ unsigned long long s_total;
@@ -38,17 +60,40 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
     unsigned long long my_total = 0ull;
     int my_max = 0;
 
-    for (long long r = (long long)blockIdx.x * groups_per_block + threadIdx.x / G; r < m; r += stride) {
-        const int row = (int)r;
-        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+    // warp-uniform loops (maxima over the groups of the warp): sub-warp groups with their
+    // own trip counts would not reconverge
+    (void)gmask;
+    const int gib = threadIdx.x / G;
+    for (long long r0 = (long long)blockIdx.x * groups_per_block + (gib & ~(32 / G - 1)); r0 < m; r0 += stride) {
+        const long long r = r0 + (gib & (32 / G - 1));
+        const bool active = r < m;
+        const int row = active ? (int)r : 0;
+        const int a0 = active ? rowptrA[row] : 0;
+        const int na = active ? rowptrA[row + 1] - a0 : 0;
+        const int max_na = __reduce_max_sync(FULL, na);
         long long s = 0;
-        for (int j = a0 + gl; j < a1; j += G) {
-            const int k = colA[j];
-            s += (long long)(__ldg(rowptrB + k + 1) - __ldg(rowptrB + k));
+        int lo = 0x7fffffff, hi = -1;
+        for (int j0 = 0; j0 < max_na; j0 += G) {
+            const int j = j0 + gl;
+            if (j < na) {
+                const int k = colA[a0 + j];
+                s += (long long)(__ldg(rowptrB + k + 1) - __ldg(rowptrB + k));
+                const int2 br = __ldg(brange + k);
+                lo = min(lo, br.x);
+                hi = max(hi, br.y);
+            }
         }
 #pragma unroll
-        for (int d = G >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(gmask, s, d, G);
-        if (gl == 0) {
+        for (int d = G >> 1; d > 0; d >>= 1) {
+            s += __shfl_xor_sync(FULL, s, d, G);
+            lo = min(lo, __shfl_xor_sync(FULL, lo, d, G));
+            hi = max(hi, __shfl_xor_sync(FULL, hi, d, G));
+        }
+        if (gl == 0 && active) {
+            int span = (hi >= lo) ? hi - lo + 1 : 0;
+            if (span > max_span) span = 0x7fffffff;   // hash path
+            rlo[row] = lo;
+            rspan[row] = span;
             int p;
             if (s > 0x7fffffffLL) {
                 p = 0x7fffffff;
@@ -58,7 +103,7 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
             }
             prod[row] = p;
             if (p <= 1) rc[row] = p;
-            atomicAdd(&s_hist[sym_bin_of(p)], 1);
+            atomicAdd(&s_hist[sym_bin_of(p, span)], 1);
             my_total += (unsigned long long)s;
             my_max = max(my_max, p);
         }
@@ -80,7 +125,8 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
     }
 }
 
-cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, int *prod, int *rc, Counters *ctr)
+cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, const int2 *brange, int *prod,
+                                int *rc, int *rlo, int *rspan, Counters *ctr)
 {
     if (m <= 0) return cudaSuccess;
     const double avg = (double)nnzA / (double)m;
@@ -92,11 +138,11 @@ cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr
     if (blocks > cap) blocks = cap;
     ++*lc.launches;
     switch (G) {
-    case 2: k_row_products<2><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
-    case 4: k_row_products<4><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
-    case 8: k_row_products<8><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
-    case 16: k_row_products<16><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
-    default: k_row_products<32><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, prod, rc, ctr); break;
+    case 2: k_row_products<2><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
+    case 4: k_row_products<4><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
+    case 8: k_row_products<8><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
+    case 16: k_row_products<16><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
+    default: k_row_products<32><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
     }
     return cudaGetLastError();
 }
@@ -112,7 +158,8 @@ cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr
 constexpr int SCATTER_ITEMS = 4;
 template <bool NUMERIC>
 __global__ void __launch_bounds__(256) k_bin_scatter(const int m, const int *__restrict__ prod,
-                                                     const int *__restrict__ rc, const BinOffsets offs,
+                                                     const int *__restrict__ rc,
+                                                     const int *__restrict__ rspan, const BinOffsets offs,
                                                      int *__restrict__ cursor, int *__restrict__ queue)
 {
     __shared__ int s_cnt[MAX_BINS];
@@ -127,7 +174,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const int m, const int *__r
         bin[it] = -1;
         if (row < m) {
             const int p = prod[row];
-            bin[it] = NUMERIC ? num_bin_of(p, rc[row]) : sym_bin_of(p);
+            bin[it] = NUMERIC ? num_bin_of(p, rc[row], rspan[row]) : sym_bin_of(p, rspan[row]);
             rank[it] = atomicAdd(&s_cnt[bin[it]], 1);
         }
     }
@@ -147,7 +194,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const int m, const int *__r
 }
 
 cudaError_t launch_bin_scatter(const LaunchCtx &lc, bool numeric, int m, const int *prod, const int *rc,
-                               const BinOffsets &offs, Counters *ctr, int *queue)
+                               const int *rspan, const BinOffsets &offs, Counters *ctr, int *queue)
 {
     if (m <= 0) return cudaSuccess;
     const int threads = 256;
@@ -155,9 +202,9 @@ cudaError_t launch_bin_scatter(const LaunchCtx &lc, bool numeric, int m, const i
     const int blocks = (int)((m + per_block - 1) / per_block);
     ++*lc.launches;
     if (numeric)
-        k_bin_scatter<true><<<blocks, threads, 0, lc.stream>>>(m, prod, rc, offs, ctr->num_cursor, queue);
+        k_bin_scatter<true><<<blocks, threads, 0, lc.stream>>>(m, prod, rc, rspan, offs, ctr->num_cursor, queue);
     else
-        k_bin_scatter<false><<<blocks, threads, 0, lc.stream>>>(m, prod, rc, offs, ctr->sym_cursor, queue);
+        k_bin_scatter<false><<<blocks, threads, 0, lc.stream>>>(m, prod, rc, rspan, offs, ctr->sym_cursor, queue);
     return cudaGetLastError();
 }
 
@@ -179,6 +226,7 @@ size_t scan_blocksum_count(int m)
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int m, const int *__restrict__ rowptrA,
                                                               const int *__restrict__ prod,
                                                               const int *__restrict__ rc,
+                                                              const int *__restrict__ rspan,
                                                               long long *__restrict__ blocksums,
                                                               Counters *__restrict__ ctr)
 {
@@ -201,7 +249,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int m, const
             const int c = rc[i];
             const int p = prod[i];
             s += c;
-            const int b = num_bin_of(p, c);
+            const int b = num_bin_of(p, c, rspan[i]);
             atomicAdd(&s_hist[b], 1);
             atomicAdd(&s_work[0][b], (unsigned long long)p);
             atomicAdd(&s_work[1][b], (unsigned long long)c);
@@ -305,12 +353,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const int m, const 
 }
 
 cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *rowptrA, const int *prod, const int *rc,
-                        int64_t *rowoff64, int *rowptr32, long long *blocksums, Counters *ctr)
+                        const int *rspan, int64_t *rowoff64, int *rowptr32, long long *blocksums, Counters *ctr)
 {
     const int nb = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
     if (nb > 0) {
         ++*lc.launches;
-        k_scan_reduce<<<nb, SCAN_THREADS, 0, lc.stream>>>(m, rowptrA, prod, rc, blocksums, ctr);
+        k_scan_reduce<<<nb, SCAN_THREADS, 0, lc.stream>>>(m, rowptrA, prod, rc, rspan, blocksums, ctr);
     }
     ++*lc.launches;
     k_scan_blocks<<<1, 1024, 0, lc.stream>>>(nb, blocksums, ctr);

@@ -35,45 +35,57 @@ k_num_group(const int *__restrict__ queue, const int count, const int *__restric
     const int gl = threadIdx.x & (G - 1);
     const int gib = threadIdx.x / G;
     const int groups_per_block = blockDim.x / G;
-    const unsigned gmask = group_mask<G>(lane);
     const int gshift = lane & ~(G - 1);
+    const unsigned gbits = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
     unsigned char *mine = smem_raw + (size_t)gib * PER_GROUP;
     VT *vals = reinterpret_cast<VT *>(mine);
     int *keys = reinterpret_cast<int *>(mine + (size_t)T * sizeof(VT));
     int *sk = keys + T;
 
-    for (int q = blockIdx.x * groups_per_block + gib; q < count; q += gridDim.x * groups_per_block) {
-        const int row = queue[q];
+    // All loops are WARP-uniform (trip counts are maxima over the 32/G groups of the warp,
+    // groups with less work are predicated off): sub-warp groups with their own loop
+    // counters never reconverge on sm_100a and then run at G/32 efficiency.
+    for (int q0 = blockIdx.x * groups_per_block + (gib & ~(32 / G - 1)); q0 < count;
+         q0 += gridDim.x * groups_per_block) {
+        const int q = q0 + (gib & (32 / G - 1));
+        const bool active = q < count;
+        const int row = active ? queue[q] : 0;
 #pragma unroll 4
         for (int s = gl; s < T; s += G) {
             keys[s] = EMPTY_KEY;
             vals[s] = VT(0);
         }
-        __syncwarp(gmask);
-        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
-        for (int base = a0; base < a1; base += G) {
+        __syncwarp();
+        const int a0 = active ? rowptrA[row] : 0;
+        const int na = active ? rowptrA[row + 1] - a0 : 0;
+        const int max_na = (G == 32) ? na : __reduce_max_sync(FULL, na);   // uniform already for G == 32
+        for (int base = 0; base < max_na; base += G) {
             const int j = base + gl;
-            int bs = 0, be = 0;
+            int bs = 0, len = 0;
             VT av = VT(0);
-            if (j < a1) {
-                const int k = colA[j];
+            if (j < na) {
+                const int k = colA[a0 + j];
                 bs = rowptrB[k];
-                be = rowptrB[k + 1];
-                av = valA[j];
+                len = rowptrB[k + 1] - bs;
+                av = valA[a0 + j];
             }
-            const int cnt = min(G, a1 - base);
+            const int cnt = min(G, max_na - base);
             for (int t = 0; t < cnt; ++t) {
-                const int s_bs = __shfl_sync(gmask, bs, t, G);
-                const int s_be = __shfl_sync(gmask, be, t, G);
-                const VT s_av = __shfl_sync(gmask, av, t, G);
-                for (int p = s_bs + gl; p < s_be; p += G) {
-                    const int c = colB[p];
-                    const VT v = s_av * valB[p];
-                    bool is_new;
-                    const int slot = table_insert<LOG2T>(keys, c, is_new);
-                    vals[slot] += v;
+                const int s_bs = __shfl_sync(FULL, bs, t, G);
+                const int s_len = __shfl_sync(FULL, len, t, G);
+                const VT s_av = __shfl_sync(FULL, av, t, G);
+                const int max_len = (G == 32) ? s_len : __reduce_max_sync(FULL, s_len);   // uniform already for G == 32
+                for (int off0 = 0; off0 < max_len; off0 += G) {
+                    const int off = off0 + gl;
+                    if (off < s_len) {
+                        const int c = colB[s_bs + off];
+                        const VT v = s_av * valB[s_bs + off];
+                        bool is_new;
+                        const int slot = table_insert<LOG2T>(keys, c, is_new);
+                        vals[slot] += v;
+                    }
                 }
-                __syncwarp(gmask);   // the next B row may hit the same slots
+                __syncwarp();   // the next B row may hit the same slots
             }
         }
         // ---- compact the occupied columns into sk[0..cnt) ----
@@ -81,11 +93,11 @@ k_num_group(const int *__restrict__ queue, const int count, const int *__restric
         for (int s0 = 0; s0 < T; s0 += G) {
             const int k = keys[s0 + gl];
             const bool occ = (k != EMPTY_KEY);
-            const unsigned bm = __ballot_sync(gmask, occ) >> gshift;
+            const unsigned bm = (__ballot_sync(FULL, occ) >> gshift) & gbits;
             if (occ) sk[cntc + __popc(bm & ((1u << gl) - 1u))] = k;
             cntc += __popc(bm);
         }
-        __syncwarp(gmask);
+        __syncwarp();
         // ---- sort ----
         if constexpr (R > 0) {
             constexpr int RR = R;
@@ -96,26 +108,32 @@ k_num_group(const int *__restrict__ queue, const int count, const int *__restric
                 const int i = gl * RR + r;
                 x[r] = (i < cntc) ? sk[i] : SORT_PAD;
             }
-            bitonic_sort_regs<G, RR>(x, gl, gmask);
-            __syncwarp(gmask);
+            bitonic_sort_regs<G, RR>(x, gl, FULL);
+            __syncwarp();
 #pragma unroll
             for (int r = 0; r < RR; ++r) sk[gl * RR + r] = x[r];
-            __syncwarp(gmask);
+            __syncwarp();
         } else {
+            // shared-memory bitonic over the largest group size of the warp (uniform stage count)
             const int np = next_pow2(cntc);
-            for (int i = cntc + gl; i < np; i += G) sk[i] = SORT_PAD;
-            __syncwarp(gmask);
-            bitonic_sort_smem_group<G>(sk, np, gl, gmask);
+            const int np_max = (G == 32) ? np : __reduce_max_sync(FULL, np);   // uniform already for G == 32
+            for (int i = cntc + gl; i < np_max; i += G) sk[i] = SORT_PAD;
+            __syncwarp();
+            bitonic_sort_smem_group<G>(sk, np_max, gl, FULL);
         }
         // ---- emit: sorted columns + their accumulated values, coalesced ----
-        const int64_t o = rowoff[row];
-        for (int i = gl; i < cntc; i += G) {
-            const int c = sk[i];
-            const int slot = table_find<LOG2T>(keys, c);
-            colC[o + i] = c;
-            valC[o + i] = vals[slot];
+        const int64_t o = active ? rowoff[row] : 0;
+        const int max_c = (G == 32) ? cntc : __reduce_max_sync(FULL, cntc);   // uniform already for G == 32
+        for (int i0 = 0; i0 < max_c; i0 += G) {
+            const int i = i0 + gl;
+            if (i < cntc) {
+                const int c = sk[i];
+                const int slot = table_find<LOG2T>(keys, c);
+                colC[o + i] = c;
+                valC[o + i] = vals[slot];
+            }
         }
-        __syncwarp(gmask);
+        __syncwarp();
     }
 }
 
@@ -308,6 +326,7 @@ static cudaError_t launch_num_group_t(const LaunchCtx &lc, const int *queue, int
     const int max_groups = 256 / G;
     if (groups > max_groups) groups = max_groups;
     const int min_groups = 32 / G;
+    groups -= groups % min_groups;   // whole warps only
     if (groups < min_groups) groups = min_groups;
     const int threads = groups * G;
     const size_t smem = per_group * groups;

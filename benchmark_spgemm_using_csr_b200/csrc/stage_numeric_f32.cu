@@ -1,5 +1,6 @@
 // stage_numeric_f32.cu -- float instantiation of the numeric kernels (stage_numeric.cuh).
 #include "stage_numeric.cuh"
+#include "stage_range_vec.cuh"
 
 namespace bhb {
 
@@ -15,6 +16,14 @@ cudaError_t launch_num_large_f32(const LaunchCtx &lc, const int *queue, int coun
 {
     return launch_num_large_t<float>(lc, queue, count, n, A, B, rowoff, colC, valC, bitmap_scratch, prefix_scratch,
                                    scratch_blocks);
+}
+
+cudaError_t launch_num_range_f32(const LaunchCtx &lc, int nsum, int nacc, const int *queue, int count, Csr A, Csr B,
+                                 const int *rlo, const int64_t *rowoff, int *colC, float *valC, WordLists wl)
+{
+    if (nacc <= 128 && range_vec_aligned(B))
+        return launch_num_range_vec_t<float>(lc, nsum, nacc, queue, count, A, B, rlo, rowoff, colC, valC, wl);
+    return launch_num_range_t<float>(lc, nsum, nacc, queue, count, A, B, rlo, rowoff, colC, valC, wl);
 }
 
 }  // namespace bhb

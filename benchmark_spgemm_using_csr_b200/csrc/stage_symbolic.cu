@@ -26,39 +26,51 @@ __global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue
     const int gl = threadIdx.x & (G - 1);
     const int gib = threadIdx.x / G;
     const int groups_per_block = blockDim.x / G;
-    const unsigned gmask = group_mask<G>(lane);
     int *keys = smem_i + gib * T;
+    (void)lane;
 
-    for (int q = blockIdx.x * groups_per_block + gib; q < count; q += gridDim.x * groups_per_block) {
-        const int row = queue[q];
+    // All loops are WARP-uniform (trip counts are maxima over the 32/G groups of the warp,
+    // groups with less work are predicated off): sub-warp groups with their own loop
+    // counters never reconverge on sm_100a and then run at G/32 efficiency.
+    for (int q0 = blockIdx.x * groups_per_block + (gib & ~(32 / G - 1)); q0 < count;
+         q0 += gridDim.x * groups_per_block) {
+        const int q = q0 + (gib & (32 / G - 1));
+        const bool active = q < count;
+        const int row = active ? queue[q] : 0;
 #pragma unroll 4
         for (int s = gl; s < T; s += G) keys[s] = EMPTY_KEY;
-        __syncwarp(gmask);
-        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        __syncwarp();
+        const int a0 = active ? rowptrA[row] : 0;
+        const int na = active ? rowptrA[row + 1] - a0 : 0;
+        const int max_na = (G == 32) ? na : __reduce_max_sync(FULL, na);   // uniform already for G == 32
         int newcnt = 0;
-        for (int base = a0; base < a1; base += G) {
+        for (int base = 0; base < max_na; base += G) {
             const int j = base + gl;
-            int bs = 0, be = 0;
-            if (j < a1) {
-                const int k = colA[j];
+            int bs = 0, len = 0;
+            if (j < na) {
+                const int k = colA[a0 + j];
                 bs = rowptrB[k];
-                be = rowptrB[k + 1];
+                len = rowptrB[k + 1] - bs;
             }
-            const int cnt = min(G, a1 - base);
+            const int cnt = min(G, max_na - base);
             for (int t = 0; t < cnt; ++t) {
-                const int s_bs = __shfl_sync(gmask, bs, t, G);
-                const int s_be = __shfl_sync(gmask, be, t, G);
-                for (int p = s_bs + gl; p < s_be; p += G) {
-                    bool is_new;
-                    table_insert<LOG2T>(keys, colB[p], is_new);
-                    newcnt += is_new;
+                const int s_bs = __shfl_sync(FULL, bs, t, G);
+                const int s_len = __shfl_sync(FULL, len, t, G);
+                const int max_len = (G == 32) ? s_len : __reduce_max_sync(FULL, s_len);   // uniform already for G == 32
+                for (int off0 = 0; off0 < max_len; off0 += G) {
+                    const int off = off0 + gl;
+                    if (off < s_len) {
+                        bool is_new;
+                        table_insert<LOG2T>(keys, colB[s_bs + off], is_new);
+                        newcnt += is_new;
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int d = G >> 1; d > 0; d >>= 1) newcnt += __shfl_xor_sync(gmask, newcnt, d, G);
-        if (gl == 0) rc[row] = newcnt;
-        __syncwarp(gmask);
+        for (int d = G >> 1; d > 0; d >>= 1) newcnt += __shfl_xor_sync(FULL, newcnt, d, G);
+        if (gl == 0 && active) rc[row] = newcnt;
+        __syncwarp();
     }
 }
 
@@ -160,6 +172,7 @@ static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int
     const int max_groups = 256 / G;
     if (groups > max_groups) groups = max_groups;
     const int min_groups = 32 / G;
+    groups -= groups % min_groups;   // whole warps only
     if (groups < min_groups) groups = min_groups;
     const int threads = groups * G;
     const size_t smem = per_group * groups;

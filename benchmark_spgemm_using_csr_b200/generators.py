@@ -18,7 +18,7 @@ import numpy as np
 
 __all__ = [
     "CSR", "poisson5pt", "poisson9pt", "poisson7pt", "poisson27pt", "rmat",
-    "uniform_rect", "random_csr", "int_values", "real_values", "transpose_pattern",
+    "uniform_rect", "random_csr", "banded_random", "int_values", "real_values", "transpose_pattern",
 ]
 
 
@@ -218,6 +218,23 @@ def random_csr(rows, cols, row_nnz, seed=1, value_seed=2, dtype=np.float64, valu
             sel += np.arange(k, dtype=np.int64)
         col[rowptr[i]:rowptr[i + 1]] = sel
     return CSR(rows, cols, rowptr.astype(np.int32), col, _values(nnz, value_seed, dtype, values))
+
+
+def banded_random(n, half_bw, row_nnz, seed=1, value_seed=2, dtype=np.float64, values="int"):
+    """n x n matrix whose row i has `row_nnz` distinct sorted columns drawn from the
+    band [i-half_bw, i+half_bw] (clipped): narrow column span per row, like FEM or
+    stencil matrices, but irregular inside the band."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    cols = []
+    for i in range(n):
+        lo, hi = max(0, i - half_bw), min(n - 1, i + half_bw)
+        k = min(int(row_nnz), hi - lo + 1)
+        sel = np.sort(rng.choice(hi - lo + 1, size=k, replace=False)) + lo
+        cols.append(sel)
+        rowptr[i + 1] = rowptr[i] + k
+    col = np.concatenate(cols).astype(np.int32) if cols else np.zeros(0, np.int32)
+    return CSR(n, n, rowptr.astype(np.int32), col, _values(col.size, value_seed, dtype, values))
 
 
 def transpose_pattern(A: CSR, value_seed=3, values="int") -> CSR:

@@ -45,8 +45,8 @@ extern "C" {
 #define BHB200_DTYPE_F32 0
 #define BHB200_DTYPE_F64 1
 
-#define BHB200_NUM_SYM_BINS 16
-#define BHB200_NUM_NUM_BINS 16
+#define BHB200_NUM_SYM_BINS 24
+#define BHB200_NUM_NUM_BINS 24
 
 typedef struct bhb200_ctx bhb200_ctx;
 

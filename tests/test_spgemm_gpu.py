@@ -93,7 +93,7 @@ P_EDGES = [0, 1, 2, 3, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 191, 1
 def test_bin_boundaries_no_duplicates(dt):
     """B = scaled identity: nnz(C_i) = products(i) = nnz(A_i), so one matrix walks
     both the symbolic (by upper bound) and numeric (by nnz(C_i)) bin edges."""
-    n = 50000
+    n = 300000          # wider than the largest shared-memory bitmap, so the long rows stay on the hash path
     sizes = np.array(P_EDGES * 2, dtype=np.int64)
     A = gen.random_csr(sizes.size, n, sizes, seed=7, dtype=dt)
     st = _check(A, _identity(n, dt), f"bin edges identity {dt.__name__}")
@@ -132,6 +132,44 @@ def test_many_empty_b_rows_in_a_small_row():
     B = gen.random_csr(k, n, lens, seed=3)
     A = gen.random_csr(64, k, 300, seed=4)
     _check(A, B, "sparse B rows")
+
+
+# ---- narrow column span: the shared-memory bitmap ("range") kernels ------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_range_kernels_large_span(dt, monkeypatch):
+    """27-point rows on a 128x128 plane span 66 053 columns -> RANGE_L bins (config 2's rows).
+    These bins are off by default (measured slower than the hash kernels at that span,
+    DESIGN.md); BHB200_RANGE=all switches them on."""
+    monkeypatch.setenv("BHB200_RANGE", "all")
+    A = gen.poisson27pt(128, 128, 6, dtype=dt)
+    st = _check(A, A, f"27pt 128x128x6 {dt.__name__}")
+    assert st["sym_bin_rows"][14] > 0 and st["num_bin_rows"][15] > 0      # SB_RANGE_L / NB_RANGE_L128
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_range_kernels_irregular_band(dt, monkeypatch):
+    """Irregular banded operands: B rows longer than a warp (tail loop), nnz(C_i) on both
+    sides of the 128 / 512 accumulator limits, rows that leave the range path for the hash
+    kernels after a range symbolic pass."""
+    monkeypatch.setenv("BHB200_RANGE", "all")
+    for n, hb, k, what in ((3000, 300, 40, "span<12K c~500"), (6000, 3000, 70, "span~12K c>512"),
+                           (20000, 9000, 9, "large span c<=128"), (20000, 9000, 12, "large span c<=512"),
+                           (20000, 9000, 45, "large span c>512")):
+        A = gen.banded_random(n, hb, k, seed=21, dtype=dt)
+        B = gen.banded_random(n, hb, k + 3, seed=22, value_seed=23, dtype=dt)
+        _check(A, B, f"banded {what} {dt.__name__}")
+
+
+def test_range_kernels_pool_overflow_fallback(monkeypatch):
+    """Word-list pool too small: the numeric range kernel must mark those rows itself."""
+    monkeypatch.setenv("BHB200_RANGE", "all")
+    monkeypatch.setenv("BHB200_DEBUG_WORDLIST_CAP", "1000")
+    A = gen.poisson27pt(40, 40, 8)
+    _check(A, A, "27pt, pool of 1000 entries")
+    B = gen.banded_random(4000, 2500, 30, seed=5)
+    _check(B, B, "banded, pool of 1000 entries")
+    monkeypatch.setenv("BHB200_DEBUG_WORDLIST_CAP", "0")
+    _check(A, A, "27pt, no pool")
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
