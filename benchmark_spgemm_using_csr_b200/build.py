@@ -98,5 +98,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DRIVER_SRC = os.path.join(os.path.dirname(HERE), "examples", "spgemm_driver.cpp")
+DRIVER_BIN = os.path.join(os.path.dirname(HERE), "examples", "spgemm")
+
+
+def build_driver(force: bool = False) -> str:
+    """The reference-compatible CLI driver (examples/spgemm_driver.cpp) on top of
+    include/bhsparse.h: `examples/spgemm -cuda -spgemm <0..4|A.mtx> [B.mtx]`."""
+    lib = build()
+    hdrs = [os.path.join(INCLUDE, "bhsparse.h"), os.path.join(INCLUDE, "bhsparse_b200.h"), DRIVER_SRC]
+    if (not force and os.path.exists(DRIVER_BIN)
+            and all(os.path.getmtime(DRIVER_BIN) >= os.path.getmtime(h) for h in hdrs)):
+        return DRIVER_BIN
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-I", INCLUDE, DRIVER_SRC, "-o", DRIVER_BIN,
+           "-L", os.path.dirname(lib), "-lbhsparse_b200", "-Wl,-rpath,$ORIGIN/../benchmark_spgemm_using_csr_b200/lib"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"driver build failed:\n{r.stdout}\n{r.stderr}")
+    return DRIVER_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--driver" in sys.argv:
+        print(build_driver(force=True))

@@ -683,6 +683,21 @@ int bhb200_get_C_device(bhb200_ctx *ctx, const int32_t **rowptr32, const int64_t
     return BHB200_SUCCESS;
 }
 
+int bhb200_copy_C_to_device(bhb200_ctx *ctx, int64_t *rowptrC64, int32_t *colC, void *valC)
+{
+    if (!ctx || !ctx->have_C) return fail(ctx, BHB200_ERR_INVALID, "copy_C_to_device before spgemm");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t s = ctx->stream;
+    if (rowptrC64)
+        CU(cudaMemcpyAsync(rowptrC64, ctx->rowoff64.p, ((size_t)ctx->m + 1) * 8, cudaMemcpyDeviceToDevice, s), "D2D rowptrC64");
+    if (colC && ctx->nnzC > 0)
+        CU(cudaMemcpyAsync(colC, ctx->colC.p, (size_t)ctx->nnzC * 4, cudaMemcpyDeviceToDevice, s), "D2D colC");
+    if (valC && ctx->nnzC > 0)
+        CU(cudaMemcpyAsync(valC, ctx->valC.p, (size_t)ctx->nnzC * vsize(ctx->dtype), cudaMemcpyDeviceToDevice, s), "D2D valC");
+    CU(cudaStreamSynchronize(s), "D2D C");
+    return BHB200_SUCCESS;
+}
+
 int bhb200_get_row_products(bhb200_ctx *ctx, int32_t *row_products)
 {
     if (!ctx || !ctx->have_data || !ctx->prod.p) return fail(ctx, BHB200_ERR_INVALID, "no row products yet");

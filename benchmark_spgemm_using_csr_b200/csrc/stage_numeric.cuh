@@ -28,7 +28,7 @@ k_num_group(const int *__restrict__ queue, const int count, const int *__restric
             int *__restrict__ colC, VT *__restrict__ valC)
 {
     constexpr int T = 1 << LOG2T;
-    constexpr int N = T / 2;                 // max nnz(C_i) of the bin
+    constexpr int N = (R > 0) ? G * R : T / 2;   // max nnz(C_i) of the bin (sort capacity); T >= 2N slots
     constexpr size_t PER_GROUP = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)N * 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -101,7 +101,7 @@ k_num_group(const int *__restrict__ queue, const int count, const int *__restric
         // ---- sort ----
         if constexpr (R > 0) {
             constexpr int RR = R;
-            static_assert(G * RR == N, "register sort must cover the bin");
+            static_assert(G * RR == N && T >= 2 * N, "register sort must cover the bin");
             int x[RR];
 #pragma unroll
             for (int r = 0; r < RR; ++r) {
@@ -321,7 +321,8 @@ static cudaError_t launch_num_group_t(const LaunchCtx &lc, const int *queue, int
                                       const int64_t *rowoff, int *colC, VT *valC)
 {
     constexpr int T = 1 << LOG2T;
-    constexpr size_t per_group = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)(T / 2) * 4;
+    constexpr int N = (R > 0) ? G * R : T / 2;
+    constexpr size_t per_group = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)N * 4;
     int groups = (int)((56 * 1024) / per_group);
     const int max_groups = 256 / G;
     if (groups > max_groups) groups = max_groups;

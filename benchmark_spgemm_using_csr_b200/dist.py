@@ -96,21 +96,14 @@ class CudaEngine:
     def result(self) -> LocalResult:
         """Copies of the device-resident result as torch tensors (device to device)."""
         nnzC = int(self.lib.bhb200_get_nnzC(self.ctx))
-        r32, r64, c, v = (ctypes.c_void_p() for _ in range(4))
-        capi.check(self.lib, self.ctx, self.lib.bhb200_get_C_device(
-            self.ctx, ctypes.byref(r32), ctypes.byref(r64), ctypes.byref(c), ctypes.byref(v)))
-        capi.check(self.lib, self.ctx, self.lib.bhb200_synchronize(self.ctx))
         dev = torch.device("cuda", self.device)
         rowptr = torch.empty(self.m + 1, dtype=torch.int64, device=dev)
-        col = torch.empty(nnzC, dtype=torch.int32, device=dev)
-        val = torch.empty(nnzC, dtype=self.vdtype, device=dev)
-        rt = torch.cuda.cudart()
-        for dst, src in ((rowptr, r64), (col, c), (val, v)):
-            if dst.numel():
-                err = rt.cudaMemcpy(dst.data_ptr(), src.value, dst.numel() * dst.element_size(), 3)  # D2D
-                if int(err) != 0:
-                    raise RuntimeError(f"cudaMemcpy D2D failed: {err}")
-        return LocalResult(nnzC, rowptr, col, val)
+        col = torch.empty(max(nnzC, 1), dtype=torch.int32, device=dev)
+        val = torch.empty(max(nnzC, 1), dtype=self.vdtype, device=dev)
+        capi.check(self.lib, self.ctx, self.lib.bhb200_copy_C_to_device(
+            self.ctx, ctypes.c_void_p(rowptr.data_ptr()), ctypes.c_void_p(col.data_ptr()),
+            ctypes.c_void_p(val.data_ptr())))
+        return LocalResult(nnzC, rowptr, col[:nnzC], val[:nnzC])
 
     def stats(self) -> dict:
         st = capi.Stats()

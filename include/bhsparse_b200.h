@@ -137,6 +137,10 @@ BHB200_API int bhb200_get_rowptrC_i64(bhb200_ctx *ctx, int64_t *rowptrC64);
  * rowptr32 is NULL-valued when nnz(C) > INT32_MAX. */
 BHB200_API int bhb200_get_C_device(bhb200_ctx *ctx, const int32_t **rowptr32, const int64_t **rowptr64,
                                    const int32_t **colC, const void **valC);
+/* Copy the result into caller-owned DEVICE buffers (rowptrC64: m+1 int64, colC / valC:
+ * nnzC entries; any may be NULL).  Device-to-device on the context's stream, complete on
+ * return. */
+BHB200_API int bhb200_copy_C_to_device(bhb200_ctx *ctx, int64_t *rowptrC64, int32_t *colC, void *valC);
 /* Host copies of the per-row intermediate-product counts (int32[m], the
  * reference's csrRowPtrCt contents, bhsparse_cuda.h:210-237) -- test hook. */
 BHB200_API int bhb200_get_row_products(bhb200_ctx *ctx, int32_t *row_products);
