@@ -270,6 +270,147 @@ __device__ __forceinline__ void bitonic_sort_smem_block(int *sk, const int N)
     }
 }
 
+// Same network with the stage loops rolled (only the per-key work is unrolled): for R >= 16
+// the fully unrolled version is 30-70 KB of straight-line code and thrashes the
+// instruction cache (measured: the R=16 CTA sort got slower when unrolled).
+template <int G, int R>
+__device__ __forceinline__ void bitonic_sort_regs_rolled(int (&x)[R], const int gl)
+{
+    constexpr int N = G * R;
+#pragma unroll 1
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j >= R; j >>= 1) {
+            const int d = j / R;
+            const bool lower = (gl & d) == 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool asc = (((gl * R + r) & k) == 0);
+                const int y = __shfl_xor_sync(FULL, x[r], d, G);
+                x[r] = (lower == asc) ? min(x[r], y) : max(x[r], y);
+            }
+        }
+#pragma unroll
+        for (int j = R >> 1; j > 0; j >>= 1) {
+            if (j < k) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & j) == 0) {
+                        const bool asc = (((gl * R + r) & k) == 0);
+                        const int lo = min(x[r], x[r + j]);
+                        const int hi = max(x[r], x[r + j]);
+                        x[r] = asc ? lo : hi;
+                        x[r + j] = asc ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Bitonic sort of N = THREADS*K keys by a whole CTA, K keys per thread in blocked order
+// (element index i = tid*K + r), ascending.  Strides < K are register compare-exchanges,
+// strides < 32*K one __shfl_xor per key, and only the log2(THREADS/32) largest strides go
+// through shared memory (`xchg`, N ints, stored transposed so the exchange is bank-conflict
+// free) -- 2 barriers for each of those instead of one per stage for an in-smem network.
+// Stage loops are rolled (see above).
+template <int K, int THREADS>
+__device__ __forceinline__ void block_bitonic_sort_regs(int (&x)[K], int *xchg)
+{
+    constexpr int N = THREADS * K;
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j >= K; j >>= 1) {
+            const int dt = j / K;   // partner thread = tid ^ dt
+            const bool lower = (tid & dt) == 0;
+            if (dt >= 32) {         // another warp: through shared memory
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < K; ++r) xchg[r * THREADS + tid] = x[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const bool asc = (((tid * K + r) & k) == 0);
+                    const int y = xchg[r * THREADS + (tid ^ dt)];
+                    x[r] = (lower == asc) ? min(x[r], y) : max(x[r], y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const bool asc = (((tid * K + r) & k) == 0);
+                    const int y = __shfl_xor_sync(FULL, x[r], dt);
+                    x[r] = (lower == asc) ? min(x[r], y) : max(x[r], y);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = K >> 1; j > 0; j >>= 1) {
+            if (j < k) {
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    if ((r & j) == 0) {
+                        const bool asc = (((tid * K + r) & k) == 0);
+                        const int lo = min(x[r], x[r + j]);
+                        const int hi = max(x[r], x[r + j]);
+                        x[r] = asc ? lo : hi;
+                        x[r + j] = asc ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Fully unrolled variant for small K (measured faster than the rolled one for K = 4).
+template <int K, int THREADS>
+__device__ __forceinline__ void block_bitonic_sort_regs_unrolled(int (&x)[K], int *xchg)
+{
+    constexpr int N = THREADS * K;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32 * K) {
+                const int dt = j / K;
+                const bool lower = (tid & dt) == 0;
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < K; ++r) xchg[r * THREADS + tid] = x[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const bool asc = (k == N) ? true : (((tid * K + r) & k) == 0);
+                    const int y = xchg[r * THREADS + (tid ^ dt)];
+                    x[r] = (lower == asc) ? min(x[r], y) : max(x[r], y);
+                }
+            } else if (j >= K) {
+                const int d = j / K;
+                const bool lower = (tid & d) == 0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const bool asc = (k == N) ? true : (((tid * K + r) & k) == 0);
+                    const int y = __shfl_xor_sync(FULL, x[r], d);
+                    x[r] = (lower == asc) ? min(x[r], y) : max(x[r], y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    if ((r & j) == 0) {
+                        const bool asc = (k == N) ? true : (((tid * K + r) & k) == 0);
+                        const int lo = min(x[r], x[r + j]);
+                        const int hi = max(x[r], x[r + j]);
+                        x[r] = asc ? lo : hi;
+                        x[r + j] = asc ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ int next_pow2(int v)
 {
     return v <= 2 ? 2 : 1 << (32 - __clz(v - 1));

@@ -108,7 +108,10 @@ k_num_group(const int *__restrict__ queue, const int count, const int *__restric
                 const int i = gl * RR + r;
                 x[r] = (i < cntc) ? sk[i] : SORT_PAD;
             }
-            bitonic_sort_regs<G, RR>(x, gl, FULL);
+            if constexpr (RR > 32)   // (rolled variant: measured slower up to R = 32)
+                bitonic_sort_regs_rolled<G, RR>(x, gl);
+            else
+                bitonic_sort_regs<G, RR>(x, gl, FULL);
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < RR; ++r) sk[gl * RR + r] = x[r];
@@ -187,10 +190,24 @@ k_num_block(const int *__restrict__ queue, const int count, const int *__restric
         }
         __syncthreads();
         const int cntc = s_cnt;
-        const int np = next_pow2(cntc);
-        for (int i = cntc + threadIdx.x; i < np; i += blockDim.x) sk[i] = SORT_PAD;
-        __syncthreads();
-        bitonic_sort_smem_block(sk, np);
+        {
+            // sort the distinct columns in registers (K per thread), see block_bitonic_sort_regs
+            constexpr int K = (T / 2) / 512;
+            int x[K];
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const int i = (int)threadIdx.x * K + r;
+                x[r] = (i < cntc) ? sk[i] : SORT_PAD;
+            }
+            if constexpr (K <= 4)
+                block_bitonic_sort_regs_unrolled<K, 512>(x, sk);
+            else
+                block_bitonic_sort_regs<K, 512>(x, sk);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < K; ++r) sk[(int)threadIdx.x * K + r] = x[r];
+            __syncthreads();
+        }
         const int64_t o = rowoff[row];
         for (int i = threadIdx.x; i < cntc; i += blockDim.x) {
             const int c = sk[i];
@@ -389,7 +406,7 @@ static cudaError_t launch_num_hash_t(const LaunchCtx &lc, int bin, int G, const 
         return G == 8 ? launch_num_group_t<VT, 8, 9, 0>(lc, queue, count, A, B, rowoff, colC, valC)
                       : launch_num_group_t<VT, 32, 9, 8>(lc, queue, count, A, B, rowoff, colC, valC);
     case NB_G1024: return launch_num_group_t<VT, 32, 10, 16>(lc, queue, count, A, B, rowoff, colC, valC);
-    case NB_G2048: return launch_num_group_t<VT, 32, 11, 0>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_G2048: return launch_num_group_t<VT, 32, 11, 32>(lc, queue, count, A, B, rowoff, colC, valC);
     case NB_B4096: return launch_num_block_t<VT, 12>(lc, queue, count, A, B, rowoff, colC, valC);
     case NB_B8192: return launch_num_block_t<VT, 13>(lc, queue, count, A, B, rowoff, colC, valC);
     case NB_B16384: return launch_num_block_t<VT, 14>(lc, queue, count, A, B, rowoff, colC, valC);
