@@ -205,8 +205,15 @@ def main():
         box = [aeqb, desc]
         dist.broadcast_object_list(box, src=0)
         aeqb, desc = box
+    # Everything timed runs on ONE explicit non-default stream: the library's kernels, the
+    # torch CUDA events and the NCCL all-gather.  (The default stream's handle is 0, which
+    # bhb200_set_stream reads as "use the context's own stream": events on the default stream
+    # would then not bracket the kernels.)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     engine = CudaEngine(local_rank)
-    engine.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    engine.use_stream(stream.cuda_stream)
+    assert stream.cuda_stream != 0
     rb = RowBlockSpGEMM(engine, dev)
     rb.setup_from_root(A, B, root=0, a_equals_b=aeqb)
     meta = rb.meta
@@ -233,12 +240,17 @@ def main():
     bin_ms_num = np.zeros(NUM_BINS)
     launches = 0
     barrier()
-    ev0.record()
+    wall0 = time.perf_counter()
+    ev0.record(stream)
     for _ in range(args.steps):
         nnz_local, off, nnz_total = rb.spgemm()
-    ev1.record()
+    ev1.record(stream)
     barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3 / args.steps
     ms = ev0.elapsed_time(ev1) / args.steps
+    # the step has host syncs inside, so device time and wall clock must agree
+    if abs(ms - wall_ms) > 0.05 * wall_ms + 0.05:
+        raise SystemExit(f"timing inconsistency: CUDA events {ms:.3f} ms/step vs wall clock {wall_ms:.3f} ms/step")
     clocks = sampler.stop() if rank == 0 else None
     st = engine.stats()                                       # last step's per-stage / per-bin times
     launches = st["kernel_launches"] * args.steps
@@ -361,7 +373,7 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms, "wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": desc, "values": "integers 1..9 (fixed seed)", "m": meta["m"], "nnzA": meta["nnzA"],
                    "products": P_total, "nnzC_rank0": int(nnz_local), "nnzC": int(nnz_total),

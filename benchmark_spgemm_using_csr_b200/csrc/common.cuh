@@ -442,6 +442,20 @@ __device__ __forceinline__ T block_sum(T v, T *red)
     return red[32];
 }
 
+// Resident CTAs per SM for a launch configuration (registers, shared memory and thread
+// limits together).  Persistent grids are sized with this: a grid sized from shared memory
+// alone ran a second, nearly empty wave when registers were the tighter limit.
+template <typename KernelT>
+inline int resident_blocks(KernelT kernel, int threads, size_t smem)
+{
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) {
+        cudaGetLastError();
+        nb = 1;
+    }
+    return nb;
+}
+
 // ---- launch interface (defined in the stage_*.cu files, called by context.cu) -
 struct Csr {
     const int *rowptr;

@@ -353,9 +353,7 @@ static cudaError_t launch_num_group_t(const LaunchCtx &lc, const int *queue, int
         if (e != cudaSuccess) return e;
     }
     long long blocks = ((long long)count + groups - 1) / groups;
-    int per_sm = (int)((200 * 1024) / smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    const int per_sm = resident_blocks(k_num_group<VT, G, LOG2T, R>, threads, smem);
     const long long cap = (long long)lc.sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     ++*lc.launches;
@@ -374,9 +372,7 @@ static cudaError_t launch_num_block_t(const LaunchCtx &lc, const int *queue, int
         cudaError_t e = cudaFuncSetAttribute(k_num_block<VT, LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    int per_sm = (int)((220 * 1024) / smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    const int per_sm = resident_blocks(k_num_block<VT, LOG2T>, 512, smem);
     long long blocks = count;
     const long long cap = (long long)lc.sm_count * per_sm;
     if (blocks > cap) blocks = cap;

@@ -92,6 +92,7 @@ cudaError_t launch_sym_range(const LaunchCtx &lc, int nsum, const int *queue, in
     const size_t smem = wb * wpb;
     cudaError_t e = cudaFuncSetAttribute(k_sym_range, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    bps = resident_blocks(k_sym_range, wpb * 32, smem);
     long long blocks = ((long long)count + wpb - 1) / wpb;
     const long long cap = (long long)lc.sm_count * bps;
     if (blocks > cap) blocks = cap;

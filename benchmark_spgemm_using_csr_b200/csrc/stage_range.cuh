@@ -299,6 +299,7 @@ static cudaError_t launch_num_range_t(const LaunchCtx &lc, int nsum, int nacc, c
     const size_t smem = wb * wpb;
     cudaError_t e = cudaFuncSetAttribute(k_num_range<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    bps = resident_blocks(k_num_range<VT>, wpb * 32, smem);
     long long blocks = ((long long)count + wpb - 1) / wpb;
     const long long cap = (long long)lc.sm_count * bps;
     if (blocks > cap) blocks = cap;

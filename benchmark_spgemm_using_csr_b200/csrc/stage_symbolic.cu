@@ -183,9 +183,7 @@ static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int
         attr_done = true;
     }
     long long blocks = ((long long)count + groups - 1) / groups;
-    int per_sm = (int)((200 * 1024) / (smem ? smem : 1));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    const int per_sm = resident_blocks(k_sym_group<G, LOG2T>, threads, smem);
     const long long cap = (long long)lc.sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     ++*lc.launches;
@@ -204,9 +202,7 @@ static cudaError_t launch_sym_block_t(const LaunchCtx &lc, const int *queue, int
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    int per_sm = (int)((200 * 1024) / smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    const int per_sm = resident_blocks(k_sym_block<LOG2T>, 512, smem);
     long long blocks = count;
     const long long cap = (long long)lc.sm_count * per_sm;
     if (blocks > cap) blocks = cap;
