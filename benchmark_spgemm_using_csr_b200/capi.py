@@ -26,7 +26,7 @@ NUM_BINS = 24
 SYM_BIN_NAMES = ["p=0", "p=1", "esc<=32", "g128", "g256", "g512", "g1024", "g2048", "g4096",
                  "b8192", "b16384", "b32768", "large", "range_s", "range_l"]
 NUM_BIN_NAMES = ["c=0", "p=1", "esc<=32", "g64", "g128", "g256", "g512", "g1024", "g2048",
-                 "b4096", "b8192", "b16384", "large", "range_s128", "range_s512", "range_l128", "range_l512"]
+                 "b4096", "b8192", "b16384", "large", "range_s128", "range_s512", "range_l128", "range_l512", "copy_ct"]
 
 # every symbol include/bhsparse_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = [
@@ -50,6 +50,7 @@ class Stats(ctypes.Structure):
         ("num_bin_products", c_int64 * NUM_BINS), ("num_bin_nnzC", c_int64 * NUM_BINS),
         ("num_bin_nnzA", c_int64 * NUM_BINS),
         ("ms_sym_bin", c_float * NUM_BINS), ("ms_num_bin", c_float * NUM_BINS),
+        ("direct_rows", c_int64), ("direct_retry_rows", c_int64), ("direct_ct_bytes", c_int64),
     ]
 
     def as_dict(self) -> dict:

@@ -72,7 +72,8 @@ enum NumBin {
     NB_RANGE_S512 = 14, // span <= SPAN_SMALL, c <= 512
     NB_RANGE_L128 = 15, // span <= SPAN_LARGE, c <= 128
     NB_RANGE_L512 = 16, // span <= SPAN_LARGE, c <= 512
-    NB_COUNT = 17
+    NB_COPY = 17,       // row already computed by the direct (single-pass) mode: Ct -> C copy only
+    NB_COUNT = 18
 };
 constexpr int MAX_BINS = 24;
 
@@ -125,12 +126,31 @@ struct Counters {
     int num_bin[MAX_BINS];
     int sym_cursor[MAX_BINS];
     int num_cursor[MAX_BINS];
+    int sample_max[MAX_BINS];      // direct mode: largest nnz(C_i) among the sampled rows of a symbolic bin
+    int retry_cnt[MAX_BINS];       // direct mode: rows of a bin that overflowed their speculated capacity
     unsigned long long num_bin_products[MAX_BINS];
     unsigned long long num_bin_nnzc[MAX_BINS];
     unsigned long long num_bin_nnza[MAX_BINS];
 };
 struct BinOffsets {
     int off[MAX_BINS + 1];
+};
+
+// Direct (single-pass) mode.  For a symbolic bin whose sampled rows all have nnz(C_i) <= cap
+// the numeric kernel runs without a symbolic pass: table sized for `cap`, each row written
+// sorted into a staging buffer at ct_off[row] (cap entries per row -- the reference's
+// over-allocated Ct, bhsparse_cuda.h:285-301), nnz(C_i) into rc[row]; after the row-pointer
+// scan k_copy_ct moves the rows to their final place (copyCt2C, :2813-2911).  A row with more
+// than `cap` distinct columns is detected while it is accumulated, gets ct_off = -1 and goes
+// to its bin's retry queue, i.e. through the ordinary symbolic + numeric kernels.
+struct DirectOut {
+    int *rc;                 // [m] nnz(C_i)
+    long long *ct_off;       // [m] first staging entry of the row, or -1
+    int *ctcol;              // staging columns
+    void *ctval;             // staging values
+    long long ct_base;       // first staging entry of this bin
+    int *retry_queue;        // this bin's retry rows
+    int *retry_cnt;          // their number (device)
 };
 
 // Word lists: the symbolic range kernel stores, per row, the non-empty 64-column words of
@@ -470,13 +490,16 @@ struct LaunchCtx {
 };
 
 // stage_count.cu
-cudaError_t launch_b_row_ranges(const LaunchCtx &lc, int k, Csr B, int2 *brange);
-cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, const int2 *brange, int *prod,
+cudaError_t launch_b_row_ranges(const LaunchCtx &lc, int k, Csr B, int4 *brange);
+cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, const int4 *brange, int *prod,
                                 int *rc, int *rlo, int *rspan, Counters *ctr);
+// spec_mask: bit b set = symbolic bin b ran in direct mode (rows with ct_off >= 0 go to NB_COPY)
 cudaError_t launch_bin_scatter(const LaunchCtx &lc, bool numeric, int m, const int *prod, const int *rc,
-                               const int *rspan, const BinOffsets &offs, Counters *ctr, int *queue);
+                               const int *rspan, unsigned spec_mask, const long long *ct_off, const BinOffsets &offs,
+                               Counters *ctr, int *queue);
 cudaError_t launch_scan(const LaunchCtx &lc, int m, const int *rowptrA, const int *prod, const int *rc,
-                        const int *rspan, int64_t *rowoff64, int *rowptr32, long long *blocksums, Counters *ctr);
+                        const int *rspan, unsigned spec_mask, const long long *ct_off, int64_t *rowoff64,
+                        int *rowptr32, long long *blocksums, Counters *ctr);
 size_t scan_blocksum_count(int m);
 // stage_small.cu
 cudaError_t launch_sym_esc(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B, int *rc);
@@ -485,7 +508,10 @@ cudaError_t launch_num_single(const LaunchCtx &lc, int dtype, const int *queue, 
 cudaError_t launch_num_esc(const LaunchCtx &lc, int dtype, const int *queue, int count, int n, Csr A, Csr B,
                            const int64_t *rowoff, int *colC, void *valC);
 // stage_symbolic.cu
-cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B, int *rc);
+// qstride > 1: only every qstride-th row of the queue (sampling); bin_max: atomicMax of the counts;
+// dcount: the number of rows is read from device memory (retry queues), `count` is its upper bound
+cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B, int *rc,
+                            int qstride = 1, int *bin_max = nullptr, const int *dcount = nullptr);
 cudaError_t launch_sym_large(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B, int *rc,
                              unsigned *bitmap_scratch, int scratch_blocks);
 // stage_numeric_f32.cu / stage_numeric_f64.cu
@@ -493,6 +519,13 @@ cudaError_t launch_num_hash_f32(const LaunchCtx &lc, int bin, int G, const int *
                                 const int64_t *rowoff, int *colC, float *valC);
 cudaError_t launch_num_hash_f64(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B,
                                 const int64_t *rowoff, int *colC, double *valC);
+// direct mode: cap in {32, 64, 128}
+cudaError_t launch_num_direct_f32(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,
+                                  DirectOut d);
+cudaError_t launch_num_direct_f64(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,
+                                  DirectOut d);
+cudaError_t launch_copy_ct(const LaunchCtx &lc, int dtype, const int *queue, int count, const int64_t *rowoff,
+                           const long long *ct_off, const int *ctcol, const void *ctval, int *colC, void *valC);
 cudaError_t launch_num_large_f32(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B,
                                  const int64_t *rowoff, int *colC, float *valC, unsigned *bitmap_scratch,
                                  int *prefix_scratch, int scratch_blocks);

@@ -77,6 +77,8 @@ struct bhb200_ctx {
     // workspace (grow-only, reused across calls)
     DevBuf prod, rc, queue, rowoff64, rowptr32, blocksums, counters, bitmap, prefix;
     DevBuf brange, rlo, rspan, wl_off, wl_cnt, wl_idx, wl_bits;   // span info + word-list pool (range kernels)
+    DevBuf ct_off, ct_col, ct_val, retry_q;                       // direct mode: staging buffer (Ct) + retry queues
+    int direct_mode = 1;                                          // BHB200_DIRECT=off disables
     size_t bitmap_zeroed_bytes = 0;
     DevBuf colC, valC;
     Counters *h_ctr = nullptr;   // pinned
@@ -205,7 +207,7 @@ int reserve_workspace(bhb200_ctx *ctx)
     CU(ctx->rowptr32.reserve(m1 * 4, &ctx->dev_bytes), "alloc rowptrC");
     CU(ctx->blocksums.reserve((scan_blocksum_count(ctx->m) + 1) * 8, &ctx->dev_bytes), "alloc scan sums");
     CU(ctx->counters.reserve(sizeof(Counters), &ctx->dev_bytes), "alloc counters");
-    CU(ctx->brange.reserve(((size_t)ctx->k + 1) * 8, &ctx->dev_bytes), "alloc B row ranges");
+    CU(ctx->brange.reserve(((size_t)ctx->k + 1) * 16, &ctx->dev_bytes), "alloc B row ranges");
     CU(ctx->rlo.reserve(m1 * 4, &ctx->dev_bytes), "alloc row min column");
     CU(ctx->rspan.reserve(m1 * 4, &ctx->dev_bytes), "alloc row span");
     return BHB200_SUCCESS;
@@ -322,6 +324,7 @@ int bhb200_create(bhb200_ctx **out, int device)
         return BHB200_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *dm = getenv("BHB200_DIRECT")) ctx->direct_mode = strcmp(dm, "off") != 0;
     if (const char *rm = getenv("BHB200_RANGE")) {
         if (!strcmp(rm, "off")) ctx->max_span = -1;
         else if (!strcmp(rm, "small")) ctx->max_span = SPAN_SMALL;
@@ -344,7 +347,8 @@ int bhb200_free_mem(bhb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     release_operands(ctx);
-    DevBuf *bufs[] = {&ctx->brange, &ctx->rlo, &ctx->rspan, &ctx->wl_off, &ctx->wl_cnt, &ctx->wl_idx, &ctx->wl_bits,
+    DevBuf *bufs[] = {&ctx->ct_off, &ctx->ct_col, &ctx->ct_val, &ctx->retry_q,
+                      &ctx->brange, &ctx->rlo, &ctx->rspan, &ctx->wl_off, &ctx->wl_cnt, &ctx->wl_idx, &ctx->wl_bits,
                       &ctx->prod, &ctx->rc, &ctx->queue, &ctx->rowoff64, &ctx->rowptr32, &ctx->blocksums,
                       &ctx->counters, &ctx->bitmap, &ctx->prefix, &ctx->colC, &ctx->valC};
     for (DevBuf *b : bufs) b->release(&ctx->dev_bytes);
@@ -436,8 +440,8 @@ int bhb200_warmup(bhb200_ctx *ctx)
     if (rc) return rc;
     LaunchCtx lc{ctx->stream, ctx->sm_count, &ctx->launches, ctx->max_span};
     CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), ctx->stream), "zero counters");
-    CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int2>()), "B row ranges kernel");
-    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int2>(), ctx->prod.as<int>(),
+    CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int4>()), "B row ranges kernel");
+    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int4>(), ctx->prod.as<int>(),
                            ctx->rc.as<int>(), ctx->rlo.as<int>(), ctx->rspan.as<int>(), ctx->counters.as<Counters>()),
        "row products kernel");
     ctx->have_C = false;
@@ -475,8 +479,8 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s), "zero counters");
     int *rlo = ctx->rlo.as<int>();
     int *rspan = ctx->rspan.as<int>();
-    CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int2>()), "B row ranges kernel");
-    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int2>(), prod, rcnt, rlo, rspan, d_ctr),
+    CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int4>()), "B row ranges kernel");
+    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int4>(), prod, rcnt, rlo, rspan, d_ctr),
        "row products kernel");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
     CU(cudaStreamSynchronize(s), "stage 1");
@@ -490,15 +494,72 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     const int G = avg_b <= 10.0 ? 8 : 32;
     BinOffsets so;
     offsets_from_counts(hc.sym_bin, so);
-    CU(launch_bin_scatter(lc, false, ctx->m, prod, rcnt, rspan, so, d_ctr, queue), "symbolic bin scatter");
+    CU(launch_bin_scatter(lc, false, ctx->m, prod, rcnt, rspan, 0u, nullptr, so, d_ctr, queue), "symbolic bin scatter");
+
+    // ---- direct (single-pass) mode: sample the group-hash bins, speculate a capacity ----
+    // (DirectOut in common.cuh).  A bin qualifies if every sampled row has nnz(C_i) <= 128.
+    unsigned spec_mask = 0;
+    int spec_cap[MAX_BINS] = {0};
+    long long spec_base[MAX_BINS] = {0};
+    long long ct_entries = 0;
+    const int SAMPLE_STRIDE = 32, SPEC_MIN_ROWS = 4096;
+    if (ctx->direct_mode) {
+        bool any = false;
+        for (int b = SB_G128; b <= SB_G4096; ++b) {
+            if (hc.sym_bin[b] < SPEC_MIN_ROWS) continue;
+            const int nsample = (hc.sym_bin[b] + SAMPLE_STRIDE - 1) / SAMPLE_STRIDE;
+            CU(launch_sym_hash(lc, b, G, queue + so.off[b], nsample, ctx->A, ctx->B, rcnt, SAMPLE_STRIDE,
+                               &d_ctr->sample_max[b]),
+               "symbolic sample");
+            any = true;
+        }
+        if (any) {
+            CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
+            CU(cudaStreamSynchronize(s), "direct-mode sampling");
+            for (int b = SB_G128; b <= SB_G4096; ++b) {
+                const int smax = ctx->h_ctr->sample_max[b];
+                if (hc.sym_bin[b] < SPEC_MIN_ROWS || smax < 1 || smax > 128) continue;
+                spec_cap[b] = smax <= 32 ? 32 : smax <= 64 ? 64 : 128;
+                spec_base[b] = ct_entries;
+                ct_entries += (long long)hc.sym_bin[b] * spec_cap[b];
+                spec_mask |= 1u << b;
+            }
+        }
+        if (spec_mask) {
+            const size_t m1 = (size_t)ctx->m + 1;
+            if (ctx->ct_off.reserve(m1 * 8, &ctx->dev_bytes) != cudaSuccess ||
+                ctx->retry_q.reserve(m1 * 4, &ctx->dev_bytes) != cudaSuccess ||
+                ctx->ct_col.reserve((size_t)ct_entries * 4 + 16, &ctx->dev_bytes) != cudaSuccess ||
+                ctx->ct_val.reserve((size_t)ct_entries * vs + 16, &ctx->dev_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                spec_mask = 0;   // no room for the staging buffer: two-pass path for everything
+            }
+        }
+    }
+    st.direct_rows = 0;
+    st.direct_ct_bytes = spec_mask ? ct_entries * (4 + (int64_t)vs) : 0;
     CU(cudaEventRecord(ctx->ev[1], s), "event");
 
-    // ---- stage 2: symbolic, one launch per non-empty bin ----
+    // ---- stage 2: symbolic, one launch per non-empty bin (direct-mode bins: the numeric kernel itself) ----
     memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
     if (hc.sym_bin[SB_ESC] > 0) CU(stamp(ctx, 0, SB_ESC), "event");
     CU(launch_sym_esc(lc, queue + so.off[SB_ESC], hc.sym_bin[SB_ESC], ctx->n, ctx->A, ctx->B, rcnt), "symbolic ESC");
     for (int b = SB_G128; b <= SB_B32768; ++b) {
         if (hc.sym_bin[b] > 0) CU(stamp(ctx, 0, b), "event");
+        if ((spec_mask >> b) & 1u) {
+            DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, spec_base[b],
+                        ctx->retry_q.as<int>() + so.off[b], &d_ctr->retry_cnt[b]};
+            if (ctx->dtype == BHB200_DTYPE_F64)
+                CU(launch_num_direct_f64(lc, spec_cap[b], G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d), "direct numeric f64");
+            else
+                CU(launch_num_direct_f32(lc, spec_cap[b], G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d), "direct numeric f32");
+            // rows that did not fit: ordinary symbolic pass, row count read on the device
+            CU(launch_sym_hash(lc, b, G, ctx->retry_q.as<int>() + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, rcnt, 1, nullptr,
+                               &d_ctr->retry_cnt[b]),
+               "symbolic retry");
+            st.direct_rows += hc.sym_bin[b];
+            continue;
+        }
         CU(launch_sym_hash(lc, b, G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, rcnt), "symbolic hash");
     }
     if (hc.sym_bin[SB_LARGE] > 0) {
@@ -530,7 +591,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(cudaEventRecord(ctx->ev[2], s), "event");
 
     // ---- stage 3: row pointers, numeric bins, exact allocation of C ----
-    CU(launch_scan(lc, ctx->m, ctx->A.rowptr, prod, rcnt, rspan, rowoff, ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
+    CU(launch_scan(lc, ctx->m, ctx->A.rowptr, prod, rcnt, rspan, spec_mask, ctx->ct_off.as<long long>(), rowoff, ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
        "row pointer scan");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
     CU(cudaStreamSynchronize(s), "stage 2/3");
@@ -547,7 +608,9 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(ctx->valC.reserve((size_t)ctx->nnzC * vs + 16, &ctx->dev_bytes), "alloc valC");
     BinOffsets no;
     offsets_from_counts(hc.num_bin, no);
-    CU(launch_bin_scatter(lc, true, ctx->m, prod, rcnt, rspan, no, d_ctr, queue), "numeric bin scatter");
+    CU(launch_bin_scatter(lc, true, ctx->m, prod, rcnt, rspan, spec_mask, ctx->ct_off.as<long long>(), no, d_ctr, queue),
+       "numeric bin scatter");
+    for (int b = 0; b < MAX_BINS; ++b) st.direct_retry_rows += hc.retry_cnt[b];
     CU(cudaEventRecord(ctx->ev[3], s), "event");
 
     // ---- stage 4: numeric, C written in place ----
@@ -599,6 +662,12 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                                         colC, (float *)valC, wl),
                    "numeric range f32");
         }
+    }
+    if (hc.num_bin[NB_COPY] > 0) {
+        CU(stamp(ctx, 1, NB_COPY), "event");
+        CU(launch_copy_ct(lc, ctx->dtype, queue + no.off[NB_COPY], hc.num_bin[NB_COPY], rowoff, ctx->ct_off.as<long long>(),
+                          ctx->ct_col.as<int>(), ctx->ct_val.p, colC, valC),
+           "Ct -> C copy");
     }
     CU(stamp(ctx, 1, MAX_BINS), "event");
     CU(cudaEventRecord(ctx->ev[4], s), "event");

@@ -140,6 +140,154 @@ k_num_group(const int *__restrict__ queue, const int count, const int *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Direct (single-pass) mode, see DirectOut in common.cuh: k_num_group without a symbolic pass
+// before it.  The table has T = 2*cap slots for rows that are EXPECTED to have at most
+// cap = G*R distinct columns; every step counts the newly inserted columns, a row that
+// exceeds cap stops inserting (so probing always terminates), is flagged and queued for the
+// two-pass path.  Rows that fit are written sorted to the staging buffer, cap entries apart.
+template <typename VT, int G, int LOG2T, int R>
+__global__ void __launch_bounds__(256, (R <= 4) ? 7 : 1)   // shared memory allows 7 CTAs/SM: stay within 32 registers
+k_num_direct(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
+             const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
+             const int *__restrict__ colB, const VT *__restrict__ valB, int *__restrict__ rc,
+             long long *__restrict__ ct_off, int *__restrict__ ctcol, VT *__restrict__ ctval,
+             const long long ct_base, int *__restrict__ retry_queue, int *__restrict__ retry_cnt)
+{
+    constexpr int T = 1 << LOG2T;
+    constexpr int N = G * R;                 // speculated capacity of a row
+    static_assert(T == 2 * N && R > 0, "direct mode uses the register sort and a half-full table");
+    constexpr size_t PER_GROUP = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)N * 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x & (G - 1);
+    const int gib = threadIdx.x / G;
+    const int groups_per_block = blockDim.x / G;
+    const int gshift = lane & ~(G - 1);
+    const unsigned gbits = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
+    unsigned char *mine = smem_raw + (size_t)gib * PER_GROUP;
+    VT *vals = reinterpret_cast<VT *>(mine);
+    int *keys = reinterpret_cast<int *>(mine + (size_t)T * sizeof(VT));
+    int *sk = keys + T;
+
+    for (int q0 = blockIdx.x * groups_per_block + (gib & ~(32 / G - 1)); q0 < count;
+         q0 += gridDim.x * groups_per_block) {
+        const int q = q0 + (gib & (32 / G - 1));
+        const bool active = q < count;
+        const int row = active ? queue[q] : 0;
+#pragma unroll 4
+        for (int s = gl; s < T; s += G) {
+            keys[s] = EMPTY_KEY;
+            vals[s] = VT(0);
+        }
+        __syncwarp();
+        const int a0 = active ? rowptrA[row] : 0;
+        const int na = active ? rowptrA[row + 1] - a0 : 0;
+        const int max_na = (G == 32) ? na : __reduce_max_sync(FULL, na);
+        int ndistinct = 0;      // group-uniform
+        bool ovf = false;       // group-uniform
+        for (int base = 0; base < max_na; base += G) {
+            const int j = base + gl;
+            int bs = 0, len = 0;
+            VT av = VT(0);
+            if (j < na) {
+                const int k = colA[a0 + j];
+                bs = rowptrB[k];
+                len = rowptrB[k + 1] - bs;
+                av = valA[a0 + j];
+            }
+            const int cnt = min(G, max_na - base);
+            for (int t = 0; t < cnt; ++t) {
+                const int s_bs = __shfl_sync(FULL, bs, t, G);
+                const int s_len = __shfl_sync(FULL, len, t, G);
+                const VT s_av = __shfl_sync(FULL, av, t, G);
+                const int max_len = (G == 32) ? s_len : __reduce_max_sync(FULL, s_len);
+                for (int off0 = 0; off0 < max_len; off0 += G) {
+                    const int off = off0 + gl;
+                    bool is_new = false;
+                    if (off < s_len && !ovf) {
+                        const int c = colB[s_bs + off];
+                        const VT v = s_av * valB[s_bs + off];
+                        const int slot = table_insert<LOG2T>(keys, c, is_new);
+                        vals[slot] += v;
+                    }
+                    // at most G new columns per sub-step: N + G < T, the table never fills up
+                    ndistinct += __popc((__ballot_sync(FULL, is_new) >> gshift) & gbits);
+                    ovf = ndistinct > N;
+                }
+                __syncwarp();
+            }
+            if (G == 32 && ovf) break;   // (warp-uniform for full-warp groups)
+        }
+        // ---- compact the occupied columns into sk[0..cnt) ----
+        int cntc = 0;
+        for (int s0 = 0; s0 < T; s0 += G) {
+            const int k = keys[s0 + gl];
+            const bool occ = (k != EMPTY_KEY) && !ovf;
+            const unsigned bm = (__ballot_sync(FULL, occ) >> gshift) & gbits;
+            if (occ) sk[cntc + __popc(bm & ((1u << gl) - 1u))] = k;
+            cntc += __popc(bm);
+        }
+        __syncwarp();
+        int x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = gl * R + r;
+            x[r] = (i < cntc) ? sk[i] : SORT_PAD;
+        }
+        if constexpr (R > 32)
+            bitonic_sort_regs_rolled<G, R>(x, gl);
+        else
+            bitonic_sort_regs<G, R>(x, gl, FULL);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; ++r) sk[gl * R + r] = x[r];
+        __syncwarp();
+        // ---- stage the sorted row (or hand it to the two-pass path) ----
+        const long long o = ct_base + (long long)q * N;
+        if (active && gl == 0) {
+            if (ovf) {
+                ct_off[row] = -1;
+                retry_queue[atomicAdd(retry_cnt, 1)] = row;
+            } else {
+                ct_off[row] = o;
+                rc[row] = cntc;
+            }
+        }
+        const int max_c = (G == 32) ? cntc : __reduce_max_sync(FULL, cntc);
+        for (int i0 = 0; i0 < max_c; i0 += G) {
+            const int i = i0 + gl;
+            if (i < cntc) {
+                const int c = sk[i];
+                const int slot = table_find<LOG2T>(keys, c);
+                ctcol[o + i] = c;
+                ctval[o + i] = vals[slot];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Staging buffer -> final C (the reference's copyCt2C, bhsparse_cuda.h:2813-2911): G lanes per row.
+template <typename VT, int G>
+__global__ void __launch_bounds__(256)
+k_copy_ct(const int *__restrict__ queue, const int count, const int64_t *__restrict__ rowoff,
+          const long long *__restrict__ ct_off, const int *__restrict__ ctcol, const VT *__restrict__ ctval,
+          int *__restrict__ colC, VT *__restrict__ valC)
+{
+    const int gl = threadIdx.x & (G - 1);
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (q >= count) return;
+    const int row = queue[q];
+    const int64_t o = rowoff[row];
+    const int n = (int)(rowoff[row + 1] - o);
+    const long long src = ct_off[row];
+    for (int i = gl; i < n; i += G) {
+        colC[o + i] = ctcol[src + i];
+        valC[o + i] = ctval[src + i];
+    }
+}
+
 template <typename VT, int LOG2T>
 __global__ void __launch_bounds__(512)
 k_num_block(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
@@ -422,6 +570,70 @@ static cudaError_t launch_num_large_t(const LaunchCtx &lc, const int *queue, int
     k_num_large<VT><<<blocks, 1024, 0, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
                                                     (const VT *)B.val, rowoff, colC, valC, bitmap_scratch,
                                                     prefix_scratch, nwords);
+    return cudaGetLastError();
+}
+
+template <typename VT, int G, int LOG2T, int R>
+static cudaError_t launch_num_direct_g(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d)
+{
+    constexpr int T = 1 << LOG2T;
+    constexpr size_t per_group = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)(G * R) * 4;
+    int groups = (int)((56 * 1024) / per_group);
+    const int max_groups = 256 / G;
+    if (groups > max_groups) groups = max_groups;
+    const int min_groups = 32 / G;
+    groups -= groups % min_groups;
+    if (groups < min_groups) groups = min_groups;
+    const int threads = groups * G;
+    const size_t smem = per_group * groups;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_num_direct<VT, G, LOG2T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    long long blocks = ((long long)count + groups - 1) / groups;
+    const long long cap = (long long)lc.sm_count * resident_blocks(k_num_direct<VT, G, LOG2T, R>, threads, smem);
+    if (blocks > cap) blocks = cap;
+    ++*lc.launches;
+    k_num_direct<VT, G, LOG2T, R><<<(int)blocks, threads, smem, lc.stream>>>(
+        queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col, (const VT *)B.val, d.rc, d.ct_off, d.ctcol,
+        (VT *)d.ctval, d.ct_base, d.retry_queue, d.retry_cnt);
+    return cudaGetLastError();
+}
+
+template <typename VT>
+static cudaError_t launch_num_direct_t(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,
+                                       DirectOut d)
+{
+    if (count <= 0) return cudaSuccess;
+    switch (cap) {
+    case 32:
+        return G == 8 ? launch_num_direct_g<VT, 8, 6, 4>(lc, queue, count, A, B, d)
+                      : launch_num_direct_g<VT, 32, 6, 1>(lc, queue, count, A, B, d);
+    case 64:
+        return G == 8 ? launch_num_direct_g<VT, 8, 7, 8>(lc, queue, count, A, B, d)
+                      : launch_num_direct_g<VT, 32, 7, 2>(lc, queue, count, A, B, d);
+    case 128:
+        return G == 8 ? launch_num_direct_g<VT, 8, 8, 16>(lc, queue, count, A, B, d)
+                      : launch_num_direct_g<VT, 32, 8, 4>(lc, queue, count, A, B, d);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <typename VT>
+static cudaError_t launch_copy_ct_t(const LaunchCtx &lc, const int *queue, int count, const int64_t *rowoff,
+                                    const long long *ct_off, const int *ctcol, const VT *ctval, int *colC, VT *valC,
+                                    double avg_row)
+{
+    if (count <= 0) return cudaSuccess;
+    const int threads = 256;
+    ++*lc.launches;
+    if (avg_row <= 12.0) {
+        const long long blocks = ((long long)count * 8 + threads - 1) / threads;
+        k_copy_ct<VT, 8><<<(int)blocks, threads, 0, lc.stream>>>(queue, count, rowoff, ct_off, ctcol, ctval, colC, valC);
+    } else {
+        const long long blocks = ((long long)count * 32 + threads - 1) / threads;
+        k_copy_ct<VT, 32><<<(int)blocks, threads, 0, lc.stream>>>(queue, count, rowoff, ct_off, ctcol, ctval, colC, valC);
+    }
     return cudaGetLastError();
 }
 

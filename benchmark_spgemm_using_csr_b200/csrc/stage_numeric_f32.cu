@@ -26,4 +26,10 @@ cudaError_t launch_num_range_f32(const LaunchCtx &lc, int nsum, int nacc, const 
     return launch_num_range_t<float>(lc, nsum, nacc, queue, count, A, B, rlo, rowoff, colC, valC, wl);
 }
 
+cudaError_t launch_num_direct_f32(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,
+                                  DirectOut d)
+{
+    return launch_num_direct_t<float>(lc, cap, G, queue, count, A, B, d);
+}
+
 }  // namespace bhb

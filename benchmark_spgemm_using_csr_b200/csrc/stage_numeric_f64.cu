@@ -26,4 +26,21 @@ cudaError_t launch_num_range_f64(const LaunchCtx &lc, int nsum, int nacc, const 
     return launch_num_range_t<double>(lc, nsum, nacc, queue, count, A, B, rlo, rowoff, colC, valC, wl);
 }
 
+cudaError_t launch_num_direct_f64(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,
+                                  DirectOut d)
+{
+    return launch_num_direct_t<double>(lc, cap, G, queue, count, A, B, d);
+}
+
+cudaError_t launch_copy_ct(const LaunchCtx &lc, int dtype, const int *queue, int count, const int64_t *rowoff,
+                           const long long *ct_off, const int *ctcol, const void *ctval, int *colC, void *valC)
+{
+    // rows per launch are not known here: pick the lane width from the bin's average row on the host side later if
+    // it matters; 32 lanes per row suit the >= 32-output rows the direct mode targets
+    return dtype ? launch_copy_ct_t<double>(lc, queue, count, rowoff, ct_off, ctcol, (const double *)ctval, colC,
+                                            (double *)valC, 64.0)
+                 : launch_copy_ct_t<float>(lc, queue, count, rowoff, ct_off, ctcol, (const float *)ctval, colC,
+                                           (float *)valC, 64.0);
+}
+
 }  // namespace bhb

@@ -15,15 +15,17 @@
 namespace bhb {
 
 template <int G, int LOG2T>
-__global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue, const int count,
+__global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue, const int count_,
                                                    const int *__restrict__ rowptrA, const int *__restrict__ colA,
                                                    const int *__restrict__ rowptrB, const int *__restrict__ colB,
-                                                   int *__restrict__ rc)
+                                                   int *__restrict__ rc, const int qstride,
+                                                   int *__restrict__ bin_max, const int *__restrict__ dcount)
 {
     constexpr int T = 1 << LOG2T;
     extern __shared__ int smem_i[];
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x & (G - 1);
+    const int count = dcount ? min(*dcount, count_) : count_;
     const int gib = threadIdx.x / G;
     const int groups_per_block = blockDim.x / G;
     int *keys = smem_i + gib * T;
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue
          q0 += gridDim.x * groups_per_block) {
         const int q = q0 + (gib & (32 / G - 1));
         const bool active = q < count;
-        const int row = active ? queue[q] : 0;
+        const int row = active ? queue[(long long)q * qstride] : 0;
 #pragma unroll 4
         for (int s = gl; s < T; s += G) keys[s] = EMPTY_KEY;
         __syncwarp();
@@ -69,7 +71,10 @@ __global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue
         }
 #pragma unroll
         for (int d = G >> 1; d > 0; d >>= 1) newcnt += __shfl_xor_sync(FULL, newcnt, d, G);
-        if (gl == 0 && active) rc[row] = newcnt;
+        if (gl == 0 && active) {
+            rc[row] = newcnt;
+            if (bin_max) atomicMax(bin_max, newcnt);
+        }
         __syncwarp();
     }
 }
@@ -163,7 +168,8 @@ __global__ void __launch_bounds__(1024) k_sym_large(const int *__restrict__ queu
 
 // ---- launchers -------------------------------------------------------------
 template <int G, int LOG2T>
-static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, int *rc)
+static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, int *rc,
+                                      int qstride, int *bin_max, const int *dcount)
 {
     constexpr int T = 1 << LOG2T;
     constexpr size_t per_group = (size_t)T * 4;
@@ -187,7 +193,8 @@ static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int
     const long long cap = (long long)lc.sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     ++*lc.launches;
-    k_sym_group<G, LOG2T><<<(int)blocks, threads, smem, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc);
+    k_sym_group<G, LOG2T><<<(int)blocks, threads, smem, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc,
+                                                                      qstride, bin_max, dcount);
     return cudaGetLastError();
 }
 
@@ -211,13 +218,14 @@ static cudaError_t launch_sym_block_t(const LaunchCtx &lc, const int *queue, int
     return cudaGetLastError();
 }
 
-cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B, int *rc)
+cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B, int *rc,
+                            int qstride, int *bin_max, const int *dcount)
 {
     if (count <= 0) return cudaSuccess;
 #define SYM_GROUP_CASE(BIN, L2T)                                                                   \
     case BIN:                                                                                      \
-        return (G == 8 && L2T <= 10) ? launch_sym_group_t<8, L2T>(lc, queue, count, A, B, rc)      \
-                                     : launch_sym_group_t<32, L2T>(lc, queue, count, A, B, rc);
+        return (G == 8 && L2T <= 10) ? launch_sym_group_t<8, L2T>(lc, queue, count, A, B, rc, qstride, bin_max, dcount)  \
+                                     : launch_sym_group_t<32, L2T>(lc, queue, count, A, B, rc, qstride, bin_max, dcount);
     switch (bin) {
         SYM_GROUP_CASE(SB_G128, 7)
         SYM_GROUP_CASE(SB_G256, 8)

@@ -77,6 +77,9 @@ typedef struct bhb200_stats {
     /* per-bin kernel times in ms (CUDA events; only with bhb200_set_profiling(ctx, 1)) */
     float ms_sym_bin[BHB200_NUM_SYM_BINS];
     float ms_num_bin[BHB200_NUM_NUM_BINS];
+    /* direct (single-pass) mode: rows computed without a symbolic pass, rows among them that
+     * overflowed the speculated capacity and were redone, size of the staging buffer (Ct) */
+    int64_t direct_rows, direct_retry_rows, direct_ct_bytes;
 } bhb200_stats;
 
 /* -- platform --------------------------------------------------------------
