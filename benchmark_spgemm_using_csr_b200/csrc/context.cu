@@ -502,7 +502,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     int spec_cap[MAX_BINS] = {0};
     long long spec_base[MAX_BINS] = {0};
     long long ct_entries = 0;
-    const int SAMPLE_STRIDE = 32, SPEC_MIN_ROWS = 4096;
+    const int SAMPLE_STRIDE = 64, SPEC_MIN_ROWS = 4096;
     if (ctx->direct_mode) {
         bool any = false;
         for (int b = SB_G128; b <= SB_G4096; ++b) {

@@ -140,7 +140,9 @@ cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr
     if (m <= 0) return cudaSuccess;
     const double avg = (double)nnzA / (double)m;
     const int threads = 256;
-    int G = avg <= 3.0 ? 2 : avg <= 6.0 ? 4 : avg <= 12.0 ? 8 : avg <= 24.0 ? 16 : 32;
+    // narrow groups on purpose: the kernel is a chain of dependent gathers (rowptrA -> colA -> B row
+    // record), so several rows per warp in flight matter more than lane utilisation
+    int G = avg <= 4.0 ? 2 : avg <= 12.0 ? 4 : avg <= 48.0 ? 8 : avg <= 160.0 ? 16 : 32;
     const long long rows_per_block = threads / G;
     long long blocks = (m + rows_per_block - 1) / rows_per_block;
     const long long cap = (long long)lc.sm_count * 64;

@@ -268,7 +268,8 @@ k_num_direct(const int *__restrict__ queue, const int count, const int *__restri
     }
 }
 
-// Staging buffer -> final C (the reference's copyCt2C, bhsparse_cuda.h:2813-2911): G lanes per row.
+// Staging buffer -> final C (the reference's copyCt2C, bhsparse_cuda.h:2813-2911): G lanes per row,
+// coalesced on both sides, four independent loads in flight per lane.
 template <typename VT, int G>
 __global__ void __launch_bounds__(256)
 k_copy_ct(const int *__restrict__ queue, const int count, const int64_t *__restrict__ rowoff,
@@ -282,9 +283,25 @@ k_copy_ct(const int *__restrict__ queue, const int count, const int64_t *__restr
     const int64_t o = rowoff[row];
     const int n = (int)(rowoff[row + 1] - o);
     const long long src = ct_off[row];
-    for (int i = gl; i < n; i += G) {
-        colC[o + i] = ctcol[src + i];
-        valC[o + i] = ctval[src + i];
+    for (int i0 = 0; i0 < n; i0 += 4 * G) {
+        int c[4];
+        VT v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * G + gl;
+            if (i < n) {
+                c[u] = ctcol[src + i];
+                v[u] = ctval[src + i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * G + gl;
+            if (i < n) {
+                colC[o + i] = c[u];
+                valC[o + i] = v[u];
+            }
+        }
     }
 }
 
