@@ -51,6 +51,7 @@ class Stats(ctypes.Structure):
         ("num_bin_nnzA", c_int64 * NUM_BINS),
         ("ms_sym_bin", c_float * NUM_BINS), ("ms_num_bin", c_float * NUM_BINS),
         ("direct_rows", c_int64), ("direct_retry_rows", c_int64), ("direct_ct_bytes", c_int64),
+        ("direct_bin_mask", c_int64),
     ]
 
     def as_dict(self) -> dict:

@@ -502,7 +502,8 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     int spec_cap[MAX_BINS] = {0};
     long long spec_base[MAX_BINS] = {0};
     long long ct_entries = 0;
-    const int SAMPLE_STRIDE = 64, SPEC_MIN_ROWS = 4096;
+    const int SAMPLE_STRIDE = 64;
+    const int SPEC_MIN_ROWS = getenv("BHB200_DEBUG_FORCE_CAP") ? 1 : 4096;
     if (ctx->direct_mode) {
         bool any = false;
         for (int b = SB_G128; b <= SB_G4096; ++b) {
@@ -516,8 +517,10 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         if (any) {
             CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
             CU(cudaStreamSynchronize(s), "direct-mode sampling");
+            const char *force = getenv("BHB200_DEBUG_FORCE_CAP");   // tests: speculate this capacity whatever the sample says
             for (int b = SB_G128; b <= SB_G4096; ++b) {
-                const int smax = ctx->h_ctr->sample_max[b];
+                int smax = ctx->h_ctr->sample_max[b];
+                if (force && hc.sym_bin[b] >= SPEC_MIN_ROWS) smax = atoi(force);
                 if (hc.sym_bin[b] < SPEC_MIN_ROWS || smax < 1 || smax > 128) continue;
                 spec_cap[b] = smax <= 32 ? 32 : smax <= 64 ? 64 : 128;
                 spec_base[b] = ct_entries;
@@ -538,6 +541,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     }
     st.direct_rows = 0;
     st.direct_ct_bytes = spec_mask ? ct_entries * (4 + (int64_t)vs) : 0;
+    st.direct_bin_mask = (int64_t)spec_mask;
     CU(cudaEventRecord(ctx->ev[1], s), "event");
 
     // ---- stage 2: symbolic, one launch per non-empty bin (direct-mode bins: the numeric kernel itself) ----

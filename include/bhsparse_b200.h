@@ -80,6 +80,7 @@ typedef struct bhb200_stats {
     /* direct (single-pass) mode: rows computed without a symbolic pass, rows among them that
      * overflowed the speculated capacity and were redone, size of the staging buffer (Ct) */
     int64_t direct_rows, direct_retry_rows, direct_ct_bytes;
+    int64_t direct_bin_mask;   /* bit b: symbolic bin b ran in direct mode (its ms_sym_bin is the numeric kernel) */
 } bhb200_stats;
 
 /* -- platform --------------------------------------------------------------

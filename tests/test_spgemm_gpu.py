@@ -172,6 +172,45 @@ def test_range_kernels_pool_overflow_fallback(monkeypatch):
     _check(A, A, "27pt, no pool")
 
 
+# ---- direct (single-pass) mode: sampled capacity, staging buffer, overflow retry --------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_direct_mode_speculation_holds(dt, monkeypatch):
+    """27-point rows: 729 products -> at most 125 outputs; the sampled bound holds for every
+    row, no symbolic pass runs for them and nothing is retried."""
+    monkeypatch.setenv("BHB200_RANGE", "off")      # (narrow-span rows would take the bitmap kernels instead)
+    A = gen.poisson27pt(40, 40, 40, dtype=dt)
+    st = _check(A, A, f"27pt 40^3 direct {dt.__name__}")
+    assert st["direct_rows"] > 0.9 * A.rows and st["direct_retry_rows"] == 0
+    assert st["num_bin_rows"][17] == st["direct_rows"]          # all of them came back through the Ct -> C copy
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("cap", ["32", "64", "128"])
+def test_direct_mode_overflow_is_retried(dt, cap, monkeypatch):
+    """Force a speculated capacity that is too small for most rows: every row that does not
+    fit must be detected and redone by the two-pass path, bit for bit."""
+    monkeypatch.setenv("BHB200_DEBUG_FORCE_CAP", cap)
+    monkeypatch.setenv("BHB200_RANGE", "off")
+    A = gen.poisson27pt(24, 24, 24, dtype=dt)
+    st = _check(A, A, f"27pt forced cap {cap} {dt.__name__}")
+    assert st["direct_rows"] > 0
+    if int(cap) < 125:
+        assert st["direct_retry_rows"] > 0
+    # irregular rows: outputs per row from a handful to several hundred inside one symbolic bin
+    R = gen.random_csr(6000, 3000, 20 + (np.arange(6000) * 7) % 40, seed=31, dtype=dt)
+    S = gen.random_csr(3000, 2500, 12, seed=32, value_seed=33, dtype=dt)
+    st = _check(R, S, f"random forced cap {cap} {dt.__name__}")
+    assert st["direct_retry_rows"] > 0
+
+
+def test_direct_mode_off_matches(monkeypatch):
+    monkeypatch.setenv("BHB200_DIRECT", "off")
+    monkeypatch.setenv("BHB200_RANGE", "off")
+    A = gen.poisson27pt(30, 30, 30)
+    st = _check(A, A, "27pt direct off")
+    assert st["direct_rows"] == 0
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_rmat_skewed(dt):
     """Graph500-style skew: long rows -> block-hash and global-bitmap bins."""
