@@ -261,6 +261,10 @@ def test_wide_column_space():
     B = CSR(k, n, (np.arange(k + 1) * 3).astype(np.int32), cols.reshape(-1), gen.int_values(3 * k, 1))
     A = gen.random_csr(200, k, (np.arange(200) % 11), seed=2)
     _check(A, B, "wide columns")
+    # mid-size rows over the same wide column space: direct mode without the packed (column, index) sort
+    A2 = gen.random_csr(5000, k, 12 + (np.arange(5000) % 20), seed=6)
+    st = _check(A2, B, "wide columns, hash bins")
+    assert st["direct_rows"] > 0
 
 
 def test_repeated_calls_and_reinit():
