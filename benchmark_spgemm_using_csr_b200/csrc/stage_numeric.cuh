@@ -305,8 +305,19 @@ k_copy_ct(const int *__restrict__ queue, const int count, const int64_t *__restr
     }
 }
 
-template <typename VT, int LOG2T>
-__global__ void __launch_bounds__(512)
+// CTAs of k_num_block<VT,LOG2T,THREADS> an SM can hold (threads and shared memory); asking the
+// compiler for that many keeps the register count from being the limiter.
+template <typename VT, int LOG2T, int THREADS>
+constexpr int num_block_min_ctas()
+{
+    constexpr int smem = (1 << LOG2T) * ((int)sizeof(VT) + 4) + (1 << LOG2T) / 2 * 4 + 1024;
+    constexpr int by_smem = (228 * 1024) / smem;   // 228 KB per SM, 1 KB reserved per CTA
+    constexpr int by_threads = 2048 / THREADS;
+    return by_smem < by_threads ? (by_smem < 1 ? 1 : by_smem) : by_threads;
+}
+
+template <typename VT, int LOG2T, int THREADS>
+__global__ void __launch_bounds__(THREADS, (num_block_min_ctas<VT, LOG2T, THREADS>()))
 k_num_block(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
             const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
             const int *__restrict__ colB, const VT *__restrict__ valB, const int64_t *__restrict__ rowoff,
@@ -357,7 +368,7 @@ k_num_block(const int *__restrict__ queue, const int count, const int *__restric
         const int cntc = s_cnt;
         {
             // sort the distinct columns in registers (K per thread), see block_bitonic_sort_regs
-            constexpr int K = (T / 2) / 512;
+            constexpr int K = (T / 2) / THREADS;
             int x[K];
 #pragma unroll
             for (int r = 0; r < K; ++r) {
@@ -365,9 +376,9 @@ k_num_block(const int *__restrict__ queue, const int count, const int *__restric
                 x[r] = (i < cntc) ? sk[i] : SORT_PAD;
             }
             if constexpr (K <= 4)
-                block_bitonic_sort_regs_unrolled<K, 512>(x, sk);
+                block_bitonic_sort_regs_unrolled<K, THREADS>(x, sk);
             else
-                block_bitonic_sort_regs<K, 512>(x, sk);
+                block_bitonic_sort_regs<K, THREADS>(x, sk);
             __syncthreads();
 #pragma unroll
             for (int r = 0; r < K; ++r) sk[(int)threadIdx.x * K + r] = x[r];
@@ -527,22 +538,22 @@ static cudaError_t launch_num_group_t(const LaunchCtx &lc, const int *queue, int
     return cudaGetLastError();
 }
 
-template <typename VT, int LOG2T>
+template <typename VT, int LOG2T, int THREADS = 512>
 static cudaError_t launch_num_block_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B,
                                       const int64_t *rowoff, int *colC, VT *valC)
 {
     constexpr int T = 1 << LOG2T;
     const size_t smem = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)(T / 2) * 4;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_num_block<VT, LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_num_block<VT, LOG2T, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int per_sm = resident_blocks(k_num_block<VT, LOG2T>, 512, smem);
+    const int per_sm = resident_blocks(k_num_block<VT, LOG2T, THREADS>, THREADS, smem);
     long long blocks = count;
     const long long cap = (long long)lc.sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     ++*lc.launches;
-    k_num_block<VT, LOG2T><<<(int)blocks, 512, smem, lc.stream>>>(
+    k_num_block<VT, LOG2T, THREADS><<<(int)blocks, THREADS, smem, lc.stream>>>(
         queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col, (const VT *)B.val, rowoff, colC, valC);
     return cudaGetLastError();
 }
@@ -566,11 +577,14 @@ static cudaError_t launch_num_hash_t(const LaunchCtx &lc, int bin, int G, const 
     case NB_G512:
         return G == 8 ? launch_num_group_t<VT, 8, 9, 0>(lc, queue, count, A, B, rowoff, colC, valC)
                       : launch_num_group_t<VT, 32, 9, 8>(lc, queue, count, A, B, rowoff, colC, valC);
-    case NB_G1024: return launch_num_group_t<VT, 32, 10, 16>(lc, queue, count, A, B, rowoff, colC, valC);
-    case NB_G2048: return launch_num_group_t<VT, 32, 11, 32>(lc, queue, count, A, B, rowoff, colC, valC);
-    case NB_B4096: return launch_num_block_t<VT, 12>(lc, queue, count, A, B, rowoff, colC, valC);
-    case NB_B8192: return launch_num_block_t<VT, 13>(lc, queue, count, A, B, rowoff, colC, valC);
-    case NB_B16384: return launch_num_block_t<VT, 14>(lc, queue, count, A, B, rowoff, colC, valC);
+    // c > 256: one CTA per row, sized so that an SM holds 2048 threads' worth of rows
+    // (R-MAT scale 20: 128/256/512/1024/1024 threads measured best for the five table sizes;
+    // a single warp per 1024/2048-slot table was 1.35-1.45x slower, profiles/r01_notes.md).
+    case NB_G1024: return launch_num_block_t<VT, 10, 128>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_G2048: return launch_num_block_t<VT, 11, 256>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_B4096: return launch_num_block_t<VT, 12, 512>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_B8192: return launch_num_block_t<VT, 13, 1024>(lc, queue, count, A, B, rowoff, colC, valC);
+    case NB_B16384: return launch_num_block_t<VT, 14, 1024>(lc, queue, count, A, B, rowoff, colC, valC);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -11,6 +11,7 @@
 // nnz(C_i) as a by-product of its numeric kernels and compacts afterwards
 // (copyCt2C, :2813-2911); counting first lets C be allocated exactly and written once.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace bhb {
 
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue
 }
 
 template <int LOG2T>
-__global__ void __launch_bounds__(512) k_sym_block(const int *__restrict__ queue, const int count,
+__global__ void __launch_bounds__(1024) k_sym_block(const int *__restrict__ queue, const int count,
                                                    const int *__restrict__ rowptrA, const int *__restrict__ colA,
                                                    const int *__restrict__ rowptrB, const int *__restrict__ colB,
                                                    int *__restrict__ rc)
@@ -182,11 +183,9 @@ static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int
     if (groups < min_groups) groups = min_groups;
     const int threads = groups * G;
     const size_t smem = per_group * groups;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (smem > 48 * 1024) {   // per device, so not cached in a static
         cudaError_t e = cudaFuncSetAttribute(k_sym_group<G, LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     long long blocks = ((long long)count + groups - 1) / groups;
     const int per_sm = resident_blocks(k_sym_group<G, LOG2T>, threads, smem);
@@ -199,22 +198,21 @@ static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int
 }
 
 template <int LOG2T>
-static cudaError_t launch_sym_block_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, int *rc)
+static cudaError_t launch_sym_block_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, int *rc,
+                                      int threads = 512)
 {
     constexpr int T = 1 << LOG2T;
     const size_t smem = (size_t)T * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_sym_block<LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
-    const int per_sm = resident_blocks(k_sym_block<LOG2T>, 512, smem);
+    const int per_sm = resident_blocks(k_sym_block<LOG2T>, threads, smem);
     long long blocks = count;
     const long long cap = (long long)lc.sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     ++*lc.launches;
-    k_sym_block<LOG2T><<<(int)blocks, 512, smem, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc);
+    k_sym_block<LOG2T><<<(int)blocks, threads, smem, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc);
     return cudaGetLastError();
 }
 
@@ -222,6 +220,12 @@ cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queu
                             int qstride, int *bin_max, const int *dcount)
 {
     if (count <= 0) return cudaSuccess;
+    // 2048/4096-slot tables: a warp per table leaves 24/12 warps per SM; a 128-thread CTA per
+    // row keeps the SM full. (Sampling and retry launches keep the group kernel.)
+    if (qstride == 1 && !bin_max && !dcount) {
+        if (bin == SB_G2048) return launch_sym_block_t<11>(lc, queue, count, A, B, rc, 128);
+        if (bin == SB_G4096) return launch_sym_block_t<12>(lc, queue, count, A, B, rc, 256);
+    }
 #define SYM_GROUP_CASE(BIN, L2T)                                                                   \
     case BIN:                                                                                      \
         return (G == 8 && L2T <= 10) ? launch_sym_group_t<8, L2T>(lc, queue, count, A, B, rc, qstride, bin_max, dcount)  \
@@ -235,7 +239,7 @@ cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queu
         SYM_GROUP_CASE(SB_G4096, 12)
     case SB_B8192: return launch_sym_block_t<13>(lc, queue, count, A, B, rc);
     case SB_B16384: return launch_sym_block_t<14>(lc, queue, count, A, B, rc);
-    case SB_B32768: return launch_sym_block_t<15>(lc, queue, count, A, B, rc);
+    case SB_B32768: return launch_sym_block_t<15>(lc, queue, count, A, B, rc, 1024);
     default: return cudaErrorInvalidValue;
     }
 #undef SYM_GROUP_CASE
