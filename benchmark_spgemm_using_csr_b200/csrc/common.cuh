@@ -174,6 +174,16 @@ __device__ __forceinline__ int hash_slot(int c)
 
 // Insert column c into an open-addressing table (linear probing).  Returns the
 // slot; is_new is true for the thread whose CAS claimed an empty slot.
+// Dynamic B-row scheduling for CTA-per-row kernels: the warps of a CTA take the row's A entries
+// from a shared-memory counter instead of a fixed stride, so a warp that drew a long B row
+// does not hold the others at the next barrier.
+__device__ __forceinline__ int take_next(int *counter, int lane)
+{
+    int j = 0;
+    if (lane == 0) j = atomicAdd(counter, 1);
+    return __shfl_sync(FULL, j, 0);
+}
+
 template <int LOG2T>
 __device__ __forceinline__ int table_insert(int *keys, int c, bool &is_new)
 {

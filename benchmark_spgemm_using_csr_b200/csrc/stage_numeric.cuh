@@ -324,23 +324,30 @@ k_num_block(const int *__restrict__ queue, const int count, const int *__restric
             int *__restrict__ colC, VT *__restrict__ valC)
 {
     constexpr int T = 1 << LOG2T;
+    constexpr int CHUNKS = T / (4 * THREADS);   // 16-byte key chunks per thread in the compaction
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_cnt;
     VT *vals = reinterpret_cast<VT *>(smem_raw);
     int *keys = reinterpret_cast<int *>(smem_raw + (size_t)T * sizeof(VT));
-    int *sk = keys + T;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int *sk = keys + T;   // no static shared memory: T=4096 must fit four CTAs per SM to the byte
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nwarps = THREADS / 32;
 
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         const int row = queue[q];
-        for (int s = threadIdx.x; s < T; s += blockDim.x) {
+        for (int s = threadIdx.x; s < T; s += THREADS) {
             keys[s] = EMPTY_KEY;
             vals[s] = VT(0);
         }
-        if (threadIdx.x == 0) s_cnt = 0;
+        if (threadIdx.x == 0) sk[0] = 0;   // next B row to take; sk[] is free until the compaction
         __syncthreads();
+        // ---- products: the warps take B rows from a shared counter. With a static
+        // warp <-> B-row assignment 31 % of the stall samples sat at the barrier below
+        // (R-MAT B rows vary from 1 to thousands of elements); taking them dynamically is
+        // 7 % faster on the whole R-MAT scale-20 product. Measured and dropped: handing long
+        // B rows to the whole CTA, fetching 32 B-row descriptors per warp at once, and
+        // keeping two B rows' loads in flight (profiles/r01_notes.md).
         const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
-        for (int j = a0 + warp; j < a1; j += nwarps) {
+        for (int j = a0 + take_next(&sk[0], lane); j < a1; j = a0 + take_next(&sk[0], lane)) {
             const int k = colA[j];
             const VT av = valA[j];
             const int bs = rowptrB[k], be = rowptrB[k + 1];
@@ -353,19 +360,44 @@ k_num_block(const int *__restrict__ queue, const int count, const int *__restric
             }
         }
         __syncthreads();
-        // compact occupied columns (order irrelevant, sorted next)
-        for (int s0 = 0; s0 < T; s0 += blockDim.x) {
-            const int s = s0 + threadIdx.x;
-            const int k = (s < T) ? keys[s] : EMPTY_KEY;
-            const bool occ = (k != EMPTY_KEY);
-            const unsigned bm = __ballot_sync(FULL, occ);
-            int basepos = 0;
-            if (lane == 0 && bm) basepos = atomicAdd(&s_cnt, __popc(bm));
-            basepos = __shfl_sync(FULL, basepos, 0);
-            if (occ) sk[basepos + __popc(bm & ((1u << lane) - 1u))] = k;
+        // ---- compact the occupied columns into sk[] (order irrelevant, sorted next):
+        // per-thread counts -> warp scan -> warp totals through sk[] -> scatter
+        int4 kc[CHUNKS];
+        int mine = 0;
+#pragma unroll
+        for (int r = 0; r < CHUNKS; ++r) {
+            kc[r] = reinterpret_cast<const int4 *>(keys)[r * THREADS + threadIdx.x];
+            mine += (kc[r].x != EMPTY_KEY) + (kc[r].y != EMPTY_KEY) + (kc[r].z != EMPTY_KEY) + (kc[r].w != EMPTY_KEY);
+        }
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (lane == 31) sk[warp] = incl;
+        __syncthreads();
+        int wt = (lane < nwarps) ? sk[lane] : 0;
+        int wincl = wt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(FULL, wincl, d);
+            if (lane >= d) wincl += y;
+        }
+        const int cntc = __shfl_sync(FULL, wincl, nwarps - 1);
+        const int wbase = __shfl_sync(FULL, wincl - wt, warp);
+        __syncthreads();
+        {
+            int pos = wbase + incl - mine;
+#pragma unroll
+            for (int r = 0; r < CHUNKS; ++r) {
+                if (kc[r].x != EMPTY_KEY) sk[pos++] = kc[r].x;
+                if (kc[r].y != EMPTY_KEY) sk[pos++] = kc[r].y;
+                if (kc[r].z != EMPTY_KEY) sk[pos++] = kc[r].z;
+                if (kc[r].w != EMPTY_KEY) sk[pos++] = kc[r].w;
+            }
         }
         __syncthreads();
-        const int cntc = s_cnt;
         {
             // sort the distinct columns in registers (K per thread), see block_bitonic_sort_regs
             constexpr int K = (T / 2) / THREADS;
@@ -404,7 +436,7 @@ k_num_large(const int *__restrict__ queue, const int count, const int *__restric
             int *__restrict__ prefix_all, const int nwords)
 {
     __shared__ int s_red[33];
-    __shared__ int s_lo, s_hi;
+    __shared__ int s_lo, s_hi, s_next[2];
     unsigned *bm = bitmap_all + (size_t)blockIdx.x * nwords;
     int *prefix = prefix_all + (size_t)blockIdx.x * nwords;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -413,6 +445,7 @@ k_num_large(const int *__restrict__ queue, const int count, const int *__restric
         if (threadIdx.x == 0) {
             s_lo = 0x7fffffff;
             s_hi = -1;
+            s_next[0] = s_next[1] = 0;
         }
         __syncthreads();
         const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
@@ -420,7 +453,7 @@ k_num_large(const int *__restrict__ queue, const int count, const int *__restric
         const int nout = (int)(rowoff[row + 1] - o);
         // ---- 1. mark the row's columns; zero the row's values ----
         int wlo = 0x7fffffff, whi = -1;
-        for (int j = a0 + warp; j < a1; j += nwarps) {
+        for (int j = a0 + take_next(&s_next[0], lane); j < a1; j = a0 + take_next(&s_next[0], lane)) {
             const int k = colA[j];
             const int bs = rowptrB[k], be = rowptrB[k + 1];
             for (int p = bs + lane; p < be; p += 32) {
@@ -486,7 +519,7 @@ k_num_large(const int *__restrict__ queue, const int count, const int *__restric
         __threadfence();
         __syncthreads();
         // ---- 3. accumulate products at their rank ----
-        for (int j = a0 + warp; j < a1; j += nwarps) {
+        for (int j = a0 + take_next(&s_next[1], lane); j < a1; j = a0 + take_next(&s_next[1], lane)) {
             const int k = colA[j];
             const VT av = valA[j];
             const int bs = rowptrB[k], be = rowptrB[k + 1];

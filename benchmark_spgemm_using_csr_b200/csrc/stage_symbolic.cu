@@ -89,15 +89,17 @@ __global__ void __launch_bounds__(1024) k_sym_block(const int *__restrict__ queu
     constexpr int T = 1 << LOG2T;
     extern __shared__ int smem_i[];
     __shared__ int s_red[33];
+    __shared__ int s_next;
     int *keys = smem_i;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         const int row = queue[q];
         for (int s = threadIdx.x; s < T; s += blockDim.x) keys[s] = EMPTY_KEY;
+        if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
         const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
         int newcnt = 0;
-        for (int j = a0 + warp; j < a1; j += nwarps) {
+        for (int j = a0 + take_next(&s_next, lane); j < a1; j = a0 + take_next(&s_next, lane)) {
             const int k = colA[j];
             const int bs = rowptrB[k], be = rowptrB[k + 1];
             for (int p = bs + lane; p < be; p += 32) {
@@ -122,19 +124,20 @@ __global__ void __launch_bounds__(1024) k_sym_large(const int *__restrict__ queu
                                                     const int nwords)
 {
     __shared__ int s_red[33];
-    __shared__ int s_lo, s_hi;
+    __shared__ int s_lo, s_hi, s_next;
     unsigned *bm = bitmap_all + (size_t)blockIdx.x * nwords;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         const int row = queue[q];
         if (threadIdx.x == 0) {
             s_lo = 0x7fffffff;
             s_hi = -1;
+            s_next = 0;
         }
         __syncthreads();
         const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
         int wlo = 0x7fffffff, whi = -1;
-        for (int j = a0 + warp; j < a1; j += nwarps) {
+        for (int j = a0 + take_next(&s_next, lane); j < a1; j = a0 + take_next(&s_next, lane)) {
             const int k = colA[j];
             const int bs = rowptrB[k], be = rowptrB[k + 1];
             for (int p = bs + lane; p < be; p += 32) {
