@@ -128,6 +128,7 @@ struct Counters {
     int num_cursor[MAX_BINS];
     int sample_max[MAX_BINS];      // direct mode: largest nnz(C_i) among the sampled rows of a symbolic bin
     int retry_cnt[MAX_BINS];       // direct mode: rows of a bin that overflowed their speculated capacity
+    unsigned long long sample_sum[MAX_BINS];   // direct mode: sum of nnz(C_i) over the sampled rows
     unsigned long long num_bin_products[MAX_BINS];
     unsigned long long num_bin_nnzc[MAX_BINS];
     unsigned long long num_bin_nnza[MAX_BINS];
@@ -151,6 +152,11 @@ struct DirectOut {
     long long ct_base;       // first staging entry of this bin
     int *retry_queue;        // this bin's retry rows
     int *retry_cnt;          // their number (device)
+    // wide bins run as two launches over the same queue, each with the table size its rows need:
+    // a launch takes the rows with p_lo < products <= p_hi and stages row q at ct_base + q*ct_stride
+    const int *prod = nullptr;
+    int p_lo = 0, p_hi = 0x7fffffff;
+    int ct_stride = 0;       // 0: the kernel's own capacity
 };
 
 // Word lists: the symbolic range kernel stores, per row, the non-empty 64-column words of
@@ -518,10 +524,11 @@ cudaError_t launch_num_single(const LaunchCtx &lc, int dtype, const int *queue, 
 cudaError_t launch_num_esc(const LaunchCtx &lc, int dtype, const int *queue, int count, int n, Csr A, Csr B,
                            const int64_t *rowoff, int *colC, void *valC);
 // stage_symbolic.cu
-// qstride > 1: only every qstride-th row of the queue (sampling); bin_max: atomicMax of the counts;
-// dcount: the number of rows is read from device memory (retry queues), `count` is its upper bound
+// qstride > 1: only every qstride-th row of the queue (sampling); bin_max / bin_sum: atomicMax / sum of
+// the counts; dcount: the number of rows is read from device memory (retry queues), `count` is its upper bound
 cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B, int *rc,
-                            int qstride = 1, int *bin_max = nullptr, const int *dcount = nullptr);
+                            int qstride = 1, int *bin_max = nullptr, const int *dcount = nullptr,
+                            unsigned long long *bin_sum = nullptr);
 cudaError_t launch_sym_large(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B, int *rc,
                              unsigned *bitmap_scratch, int scratch_blocks);
 // stage_numeric_f32.cu / stage_numeric_f64.cu
@@ -529,7 +536,8 @@ cudaError_t launch_num_hash_f32(const LaunchCtx &lc, int bin, int G, const int *
                                 const int64_t *rowoff, int *colC, float *valC);
 cudaError_t launch_num_hash_f64(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B,
                                 const int64_t *rowoff, int *colC, double *valC);
-// direct mode: cap in {32, 64, 128}
+// direct mode: cap in {32, 64, 128} speculated (rows may overflow into the retry queue), or
+// {256, ..., 8192} for bins whose product bound is below cap (no overflow possible)
 cudaError_t launch_num_direct_f32(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,
                                   DirectOut d);
 cudaError_t launch_num_direct_f64(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,

@@ -79,6 +79,7 @@ struct bhb200_ctx {
     DevBuf brange, rlo, rspan, wl_off, wl_cnt, wl_idx, wl_bits;   // span info + word-list pool (range kernels)
     DevBuf ct_off, ct_col, ct_val, retry_q;                       // direct mode: staging buffer (Ct) + retry queues
     int direct_mode = 1;                                          // BHB200_DIRECT=off disables
+    int direct_wide = 1;                                          // BHB200_DIRECT=tight: speculated capacities <= 128 only
     size_t bitmap_zeroed_bytes = 0;
     DevBuf colC, valC;
     Counters *h_ctr = nullptr;   // pinned
@@ -324,7 +325,10 @@ int bhb200_create(bhb200_ctx **out, int device)
         return BHB200_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    if (const char *dm = getenv("BHB200_DIRECT")) ctx->direct_mode = strcmp(dm, "off") != 0;
+    if (const char *dm = getenv("BHB200_DIRECT")) {
+        ctx->direct_mode = strcmp(dm, "off") != 0;
+        ctx->direct_wide = strcmp(dm, "tight") != 0;
+    }
     if (const char *rm = getenv("BHB200_RANGE")) {
         if (!strcmp(rm, "off")) ctx->max_span = -1;
         else if (!strcmp(rm, "small")) ctx->max_span = SPAN_SMALL;
@@ -496,21 +500,29 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     offsets_from_counts(hc.sym_bin, so);
     CU(launch_bin_scatter(lc, false, ctx->m, prod, rcnt, rspan, 0u, nullptr, so, d_ctr, queue), "symbolic bin scatter");
 
-    // ---- direct (single-pass) mode: sample the group-hash bins, speculate a capacity ----
-    // (DirectOut in common.cuh).  A bin qualifies if every sampled row has nnz(C_i) <= 128.
+    // ---- direct (single-pass) mode: sample the group-hash bins, pick a staging capacity ----
+    // (DirectOut in common.cuh). Two cases per bin:
+    //  * tight: every sampled row has nnz(C_i) <= 128 -> speculate 32/64/128 entries per row,
+    //    rows that overflow go through the two-pass path (stencils: 1728 products -> 125);
+    //  * wide: the sampled rows barely compress (mean nnz(C_i) >= a quarter of the bin's table
+    //    capacity, R-MAT: nnz(C_i) ~ products) -> the numeric kernel would use the table the
+    //    product bound dictates anyway, so it runs once, staged, and the symbolic pass is
+    //    skipped; the bound is below the capacity, nothing can overflow.
     unsigned spec_mask = 0;
     int spec_cap[MAX_BINS] = {0};
+    bool spec_wide[MAX_BINS] = {false};
     long long spec_base[MAX_BINS] = {0};
     long long ct_entries = 0;
     const int SAMPLE_STRIDE = 64;
     const int SPEC_MIN_ROWS = getenv("BHB200_DEBUG_FORCE_CAP") ? 1 : 4096;
+    static const int WIDE_CAP[7] = {128, 256, 512, 1024, 2048, 4096, 8192};   // SB_G128 .. SB_B8192
     if (ctx->direct_mode) {
         bool any = false;
         for (int b = SB_G128; b <= SB_G4096; ++b) {
             if (hc.sym_bin[b] < SPEC_MIN_ROWS) continue;
             const int nsample = (hc.sym_bin[b] + SAMPLE_STRIDE - 1) / SAMPLE_STRIDE;
             CU(launch_sym_hash(lc, b, G, queue + so.off[b], nsample, ctx->A, ctx->B, rcnt, SAMPLE_STRIDE,
-                               &d_ctr->sample_max[b]),
+                               &d_ctr->sample_max[b], nullptr, &d_ctr->sample_sum[b]),
                "symbolic sample");
             any = true;
         }
@@ -518,14 +530,56 @@ int bhb200_spgemm(bhb200_ctx *ctx)
             CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
             CU(cudaStreamSynchronize(s), "direct-mode sampling");
             const char *force = getenv("BHB200_DEBUG_FORCE_CAP");   // tests: speculate this capacity whatever the sample says
-            for (int b = SB_G128; b <= SB_G4096; ++b) {
-                int smax = ctx->h_ctr->sample_max[b];
-                if (force && hc.sym_bin[b] >= SPEC_MIN_ROWS) smax = atoi(force);
-                if (hc.sym_bin[b] < SPEC_MIN_ROWS || smax < 1 || smax > 128) continue;
-                spec_cap[b] = smax <= 32 ? 32 : smax <= 64 ? 64 : 128;
+            bool wide_above = false;
+            for (int b = SB_G128; b <= SB_B8192; ++b) {
+                if (hc.sym_bin[b] <= 0) continue;
+                if (b == SB_B8192) {
+                    // not sampled (the group kernels stop at 4096 slots): follows its neighbour
+                    if (!wide_above) continue;
+                    spec_cap[b] = WIDE_CAP[b - SB_G128];
+                    spec_wide[b] = true;
+                } else {
+                    wide_above = false;
+                    int smax = ctx->h_ctr->sample_max[b];
+                    if (force && hc.sym_bin[b] >= SPEC_MIN_ROWS) smax = atoi(force);
+                    if (hc.sym_bin[b] < SPEC_MIN_ROWS || smax < 1) continue;
+                    const int nsample = (hc.sym_bin[b] + SAMPLE_STRIDE - 1) / SAMPLE_STRIDE;
+                    const double mean = (double)ctx->h_ctr->sample_sum[b] / nsample;
+                    const int wcap = WIDE_CAP[b - SB_G128];
+                    if (smax <= 128) {
+                        spec_cap[b] = smax <= 32 ? 32 : smax <= 64 ? 64 : 128;
+                    } else if (ctx->direct_wide && !force && mean * 4.0 >= wcap) {
+                        spec_cap[b] = wcap;
+                        spec_wide[b] = true;
+                        wide_above = true;
+                    } else {
+                        continue;
+                    }
+                }
                 spec_base[b] = ct_entries;
                 ct_entries += (long long)hc.sym_bin[b] * spec_cap[b];
                 spec_mask |= 1u << b;
+            }
+        }
+        // the wide staging buffer must not crowd out C itself (at most `products` entries)
+        if (spec_mask && ((size_t)ct_entries * 4 + 16 > ctx->ct_col.cap || (size_t)ct_entries * vs + 16 > ctx->ct_val.cap)) {
+            // (only when the staging buffer has to grow: cudaMemGetInfo can take milliseconds)
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const double avail = (double)free_b + (double)ctx->ct_col.cap + (double)ctx->ct_val.cap +
+                                 (double)ctx->colC.cap + (double)ctx->valC.cap;
+            const double need = ((double)ct_entries + (double)st.products) * (4.0 + vs);
+            if (need > 0.9 * avail) {
+                ct_entries = 0;
+                for (int b = SB_G128; b <= SB_B8192; ++b) {
+                    if (!((spec_mask >> b) & 1u)) continue;
+                    if (spec_wide[b]) {
+                        spec_mask &= ~(1u << b);
+                        continue;
+                    }
+                    spec_base[b] = ct_entries;
+                    ct_entries += (long long)hc.sym_bin[b] * spec_cap[b];
+                }
             }
         }
         if (spec_mask) {
@@ -553,14 +607,29 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         if ((spec_mask >> b) & 1u) {
             DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, spec_base[b],
                         ctx->retry_q.as<int>() + so.off[b], &d_ctr->retry_cnt[b]};
-            if (ctx->dtype == BHB200_DTYPE_F64)
-                CU(launch_num_direct_f64(lc, spec_cap[b], G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d), "direct numeric f64");
-            else
-                CU(launch_num_direct_f32(lc, spec_cap[b], G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d), "direct numeric f32");
+            // wide bins: the rows up to half the capacity run with the half-size table
+            const int passes = spec_wide[b] ? 2 : 1;
+            for (int pass = 0; pass < passes; ++pass) {
+                int cap = spec_cap[b];
+                if (spec_wide[b]) {
+                    d.prod = prod;
+                    d.ct_stride = spec_cap[b];
+                    d.p_lo = pass == 0 ? 0 : spec_cap[b] / 2;
+                    d.p_hi = pass == 0 ? spec_cap[b] / 2 : 0x7fffffff;
+                    if (pass == 0) cap = spec_cap[b] / 2;
+                }
+                if (ctx->dtype == BHB200_DTYPE_F64)
+                    CU(launch_num_direct_f64(lc, cap, spec_wide[b] ? 32 : G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d),
+                       "direct numeric f64");
+                else
+                    CU(launch_num_direct_f32(lc, cap, spec_wide[b] ? 32 : G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d),
+                       "direct numeric f32");
+            }
             // rows that did not fit: ordinary symbolic pass, row count read on the device
-            CU(launch_sym_hash(lc, b, G, ctx->retry_q.as<int>() + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, rcnt, 1, nullptr,
-                               &d_ctr->retry_cnt[b]),
-               "symbolic retry");
+            if (!spec_wide[b])
+                CU(launch_sym_hash(lc, b, G, ctx->retry_q.as<int>() + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, rcnt, 1,
+                                   nullptr, &d_ctr->retry_cnt[b]),
+                   "symbolic retry");
             st.direct_rows += hc.sym_bin[b];
             continue;
         }

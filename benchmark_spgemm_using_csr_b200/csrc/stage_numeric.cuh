@@ -146,14 +146,17 @@ k_num_group(const int *__restrict__ queue, const int count, const int *__restric
 // cap = G*R distinct columns; every step counts the newly inserted columns, a row that
 // exceeds cap stops inserting (so probing always terminates), is flagged and queued for the
 // two-pass path.  Rows that fit are written sorted to the staging buffer, cap entries apart.
-template <typename VT, int G, int LOG2T, int R>
-__global__ void __launch_bounds__(256, (R <= 4) ? 7 : 1)   // shared memory allows 7 CTAs/SM: stay within 32 registers
+// FILTER (full-warp groups only): take the rows with p_lo < products <= p_hi, stage ct_stride apart.
+template <typename VT, int G, int LOG2T, int R, bool FILTER = false>
+__global__ void __launch_bounds__(256, (R <= 4) ? 7 : (G == 32 && R == 8) ? 4 : 1)   // CTAs/SM shared memory allows: keep the registers below that
 k_num_direct(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
              const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
              const int *__restrict__ colB, const VT *__restrict__ valB, int *__restrict__ rc,
              long long *__restrict__ ct_off, int *__restrict__ ctcol, VT *__restrict__ ctval,
-             const long long ct_base, int *__restrict__ retry_queue, int *__restrict__ retry_cnt)
+             const long long ct_base, int *__restrict__ retry_queue, int *__restrict__ retry_cnt,
+             const int *__restrict__ prod = nullptr, const int p_lo = 0, const int p_hi = 0, const int ct_stride = 0)
 {
+    static_assert(!FILTER || G == 32, "row filter: full-warp groups");
     constexpr int T = 1 << LOG2T;
     constexpr int N = G * R;                 // speculated capacity of a row
     static_assert(T == 2 * N && R > 0, "direct mode uses the register sort and a half-full table");
@@ -175,6 +178,10 @@ k_num_direct(const int *__restrict__ queue, const int count, const int *__restri
         const int q = q0 + (gib & (32 / G - 1));
         const bool active = q < count;
         const int row = active ? queue[q] : 0;
+        if constexpr (FILTER) {
+            const int p = prod[row];
+            if (p <= p_lo || p > p_hi) continue;   // warp-uniform: one row per warp
+        }
 #pragma unroll 4
         for (int s = gl; s < T; s += G) {
             keys[s] = EMPTY_KEY;
@@ -244,7 +251,7 @@ k_num_direct(const int *__restrict__ queue, const int count, const int *__restri
         for (int r = 0; r < R; ++r) sk[gl * R + r] = x[r];
         __syncwarp();
         // ---- stage the sorted row (or hand it to the two-pass path) ----
-        const long long o = ct_base + (long long)q * N;
+        const long long o = ct_base + (long long)q * (FILTER ? ct_stride : N);
         if (active && gl == 0) {
             if (ovf) {
                 ct_off[row] = -1;
@@ -316,12 +323,17 @@ constexpr int num_block_min_ctas()
     return by_smem < by_threads ? (by_smem < 1 ? 1 : by_smem) : by_threads;
 }
 
-template <typename VT, int LOG2T, int THREADS>
+// DIRECT: single-pass mode for the rows of a symbolic bin with p_lo < products <= p_hi <= T/2:
+// the row is staged at ct_base + q*ct_stride in the staging buffer (colC/valC then point to
+// it), its length and staging offset are recorded for the scan and k_copy_ct; rowoff is not read.
+template <typename VT, int LOG2T, int THREADS, bool DIRECT = false>
 __global__ void __launch_bounds__(THREADS, (num_block_min_ctas<VT, LOG2T, THREADS>()))
 k_num_block(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
             const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
             const int *__restrict__ colB, const VT *__restrict__ valB, const int64_t *__restrict__ rowoff,
-            int *__restrict__ colC, VT *__restrict__ valC)
+            int *__restrict__ colC, VT *__restrict__ valC, int *__restrict__ rc = nullptr,
+            long long *__restrict__ ct_off = nullptr, const long long ct_base = 0,
+            const int *__restrict__ prod = nullptr, const int p_lo = 0, const int p_hi = 0, const int ct_stride = 0)
 {
     constexpr int T = 1 << LOG2T;
     constexpr int CHUNKS = T / (4 * THREADS);   // 16-byte key chunks per thread in the compaction
@@ -334,6 +346,10 @@ k_num_block(const int *__restrict__ queue, const int count, const int *__restric
 
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         const int row = queue[q];
+        if constexpr (DIRECT) {
+            const int p = prod[row];
+            if (p <= p_lo || p > p_hi) continue;   // CTA-uniform
+        }
         for (int s = threadIdx.x; s < T; s += THREADS) {
             keys[s] = EMPTY_KEY;
             vals[s] = VT(0);
@@ -416,7 +432,16 @@ k_num_block(const int *__restrict__ queue, const int count, const int *__restric
             for (int r = 0; r < K; ++r) sk[(int)threadIdx.x * K + r] = x[r];
             __syncthreads();
         }
-        const int64_t o = rowoff[row];
+        int64_t o;
+        if constexpr (DIRECT) {
+            o = ct_base + (int64_t)q * ct_stride;
+            if (threadIdx.x == 0) {
+                rc[row] = cntc;
+                ct_off[row] = o;
+            }
+        } else {
+            o = rowoff[row];
+        }
         for (int i = threadIdx.x; i < cntc; i += blockDim.x) {
             const int c = sk[i];
             const int slot = table_find<LOG2T>(keys, c);
@@ -637,9 +662,38 @@ static cudaError_t launch_num_large_t(const LaunchCtx &lc, const int *queue, int
     return cudaGetLastError();
 }
 
+template <typename VT, int LOG2T, int R>
+static cudaError_t launch_num_direct_filtered(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d)
+{
+    constexpr int T = 1 << LOG2T;
+    constexpr size_t per_group = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)(32 * R) * 4;
+    int groups = (int)((56 * 1024) / per_group);
+    if (groups > 8) groups = 8;
+    if (groups < 1) groups = 1;
+    const int threads = groups * 32;
+    const size_t smem = per_group * groups;
+    auto kern = k_num_direct<VT, 32, LOG2T, R, true>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    long long blocks = ((long long)count + groups - 1) / groups;
+    const long long cap = (long long)lc.sm_count * resident_blocks(kern, threads, smem);
+    if (blocks > cap) blocks = cap;
+    ++*lc.launches;
+    kern<<<(int)blocks, threads, smem, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
+                                                    (const VT *)B.val, d.rc, d.ct_off, d.ctcol, (VT *)d.ctval, d.ct_base,
+                                                    d.retry_queue, d.retry_cnt, d.prod, d.p_lo, d.p_hi,
+                                                    d.ct_stride ? d.ct_stride : 32 * R);
+    return cudaGetLastError();
+}
+
 template <typename VT, int G, int LOG2T, int R>
 static cudaError_t launch_num_direct_g(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d)
 {
+    if constexpr (G == 32) {
+        if (d.prod) return launch_num_direct_filtered<VT, LOG2T, R>(lc, queue, count, A, B, d);
+    }
     constexpr int T = 1 << LOG2T;
     constexpr size_t per_group = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)(G * R) * 4;
     int groups = (int)((56 * 1024) / per_group);
@@ -664,12 +718,39 @@ static cudaError_t launch_num_direct_g(const LaunchCtx &lc, const int *queue, in
     return cudaGetLastError();
 }
 
+template <typename VT, int LOG2T, int THREADS>
+static cudaError_t launch_num_block_direct_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d)
+{
+    constexpr int T = 1 << LOG2T;
+    const size_t smem = (size_t)T * sizeof(VT) + (size_t)T * 4 + (size_t)(T / 2) * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_num_block<VT, LOG2T, THREADS, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int per_sm = resident_blocks(k_num_block<VT, LOG2T, THREADS, true>, THREADS, smem);
+    long long blocks = count;
+    const long long cap = (long long)lc.sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    ++*lc.launches;
+    k_num_block<VT, LOG2T, THREADS, true><<<(int)blocks, THREADS, smem, lc.stream>>>(
+        queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col, (const VT *)B.val, nullptr, d.ctcol,
+        (VT *)d.ctval, d.rc, d.ct_off, d.ct_base, d.prod, d.p_lo, d.p_hi, d.ct_stride ? d.ct_stride : T / 2);
+    return cudaGetLastError();
+}
+
 template <typename VT>
 static cudaError_t launch_num_direct_t(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,
                                        DirectOut d)
 {
     if (count <= 0) return cudaSuccess;
     switch (cap) {
+    case 256: return launch_num_direct_g<VT, 32, 9, 8>(lc, queue, count, A, B, d);
+    case 512: return launch_num_block_direct_t<VT, 10, 128>(lc, queue, count, A, B, d);
+    case 1024: return launch_num_block_direct_t<VT, 11, 256>(lc, queue, count, A, B, d);
+    case 2048: return launch_num_block_direct_t<VT, 12, 512>(lc, queue, count, A, B, d);
+    case 4096: return launch_num_block_direct_t<VT, 13, 1024>(lc, queue, count, A, B, d);
+    case 8192: return launch_num_block_direct_t<VT, 14, 1024>(lc, queue, count, A, B, d);
     case 32:
         return G == 8 ? launch_num_direct_g<VT, 8, 6, 4>(lc, queue, count, A, B, d)
                       : launch_num_direct_g<VT, 32, 6, 1>(lc, queue, count, A, B, d);

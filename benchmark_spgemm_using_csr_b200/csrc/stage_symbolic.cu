@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue
                                                    const int *__restrict__ rowptrA, const int *__restrict__ colA,
                                                    const int *__restrict__ rowptrB, const int *__restrict__ colB,
                                                    int *__restrict__ rc, const int qstride,
-                                                   int *__restrict__ bin_max, const int *__restrict__ dcount)
+                                                   int *__restrict__ bin_max, const int *__restrict__ dcount,
+                                                   unsigned long long *__restrict__ bin_sum)
 {
     constexpr int T = 1 << LOG2T;
     extern __shared__ int smem_i[];
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) k_sym_group(const int *__restrict__ queue
         if (gl == 0 && active) {
             rc[row] = newcnt;
             if (bin_max) atomicMax(bin_max, newcnt);
+            if (bin_sum) atomicAdd(bin_sum, (unsigned long long)newcnt);
         }
         __syncwarp();
     }
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(1024) k_sym_large(const int *__restrict__ queu
 // ---- launchers -------------------------------------------------------------
 template <int G, int LOG2T>
 static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, int *rc,
-                                      int qstride, int *bin_max, const int *dcount)
+                                      int qstride, int *bin_max, const int *dcount, unsigned long long *bin_sum)
 {
     constexpr int T = 1 << LOG2T;
     constexpr size_t per_group = (size_t)T * 4;
@@ -196,7 +198,7 @@ static cudaError_t launch_sym_group_t(const LaunchCtx &lc, const int *queue, int
     if (blocks > cap) blocks = cap;
     ++*lc.launches;
     k_sym_group<G, LOG2T><<<(int)blocks, threads, smem, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc,
-                                                                      qstride, bin_max, dcount);
+                                                                      qstride, bin_max, dcount, bin_sum);
     return cudaGetLastError();
 }
 
@@ -220,7 +222,7 @@ static cudaError_t launch_sym_block_t(const LaunchCtx &lc, const int *queue, int
 }
 
 cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queue, int count, Csr A, Csr B, int *rc,
-                            int qstride, int *bin_max, const int *dcount)
+                            int qstride, int *bin_max, const int *dcount, unsigned long long *bin_sum)
 {
     if (count <= 0) return cudaSuccess;
     // 2048/4096-slot tables: a warp per table leaves 24/12 warps per SM; a 128-thread CTA per
@@ -231,8 +233,8 @@ cudaError_t launch_sym_hash(const LaunchCtx &lc, int bin, int G, const int *queu
     }
 #define SYM_GROUP_CASE(BIN, L2T)                                                                   \
     case BIN:                                                                                      \
-        return (G == 8 && L2T <= 10) ? launch_sym_group_t<8, L2T>(lc, queue, count, A, B, rc, qstride, bin_max, dcount)  \
-                                     : launch_sym_group_t<32, L2T>(lc, queue, count, A, B, rc, qstride, bin_max, dcount);
+        return (G == 8 && L2T <= 10) ? launch_sym_group_t<8, L2T>(lc, queue, count, A, B, rc, qstride, bin_max, dcount, bin_sum)  \
+                                     : launch_sym_group_t<32, L2T>(lc, queue, count, A, B, rc, qstride, bin_max, dcount, bin_sum);
     switch (bin) {
         SYM_GROUP_CASE(SB_G128, 7)
         SYM_GROUP_CASE(SB_G256, 8)

@@ -203,6 +203,24 @@ def test_direct_mode_overflow_is_retried(dt, cap, monkeypatch):
     assert st["direct_retry_rows"] > 0
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_direct_mode_wide_bins(dt, monkeypatch):
+    """Rows that barely compress (wide random column space): the sampled mean nnz(C_i) is close
+    to the product bound, so the bins up to 6144 products run single-pass with the capacity the
+    bound dictates (group kernel for 256, CTA kernels for 512..8192) and skip the symbolic pass."""
+    per_row = np.array([12, 24, 48, 96, 150, 250, 400])[np.arange(7 * 4500) % 7]
+    A = gen.random_csr(7 * 4500, 20000, per_row, seed=41, dtype=dt)
+    B = gen.random_csr(20000, 3_000_000, 12, seed=42, value_seed=43, dtype=dt)
+    st = _check(A, B, f"wide direct {dt.__name__}")
+    mask = st["direct_bin_mask"]
+    assert all((mask >> b) & 1 for b in range(4, 10)), bin(mask)      # SB_G256 .. SB_B8192
+    assert st["direct_retry_rows"] == 0 and st["direct_rows"] >= 6 * 4500
+    assert st["num_bin_rows"][17] == st["direct_rows"]
+    monkeypatch.setenv("BHB200_DIRECT", "tight")
+    st = _check(A, B, f"wide direct disabled {dt.__name__}")
+    assert all(not ((st["direct_bin_mask"] >> b) & 1) for b in range(4, 10))
+
+
 def test_direct_mode_off_matches(monkeypatch):
     monkeypatch.setenv("BHB200_DIRECT", "off")
     monkeypatch.setenv("BHB200_RANGE", "off")
