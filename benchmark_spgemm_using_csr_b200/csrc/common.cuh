@@ -180,6 +180,12 @@ __device__ __forceinline__ int hash_slot(int c)
 
 // Insert column c into an open-addressing table (linear probing).  Returns the
 // slot; is_new is true for the thread whose CAS claimed an empty slot.
+// Words of a per-CTA column bitmap for n columns (large-row kernels), padded to 16 bytes.
+__host__ __device__ __forceinline__ int large_nwords(int n)
+{
+    return (int)((((long long)n + 31) / 32 + 3) & ~3LL);
+}
+
 // Dynamic B-row scheduling for CTA-per-row kernels: the warps of a CTA take the row's A entries
 // from a shared-memory counter instead of a fixed stride, so a warp that drew a long B row
 // does not hold the others at the next barrier.
@@ -189,6 +195,44 @@ __device__ __forceinline__ int take_next(int *counter, int lane)
     if (lane == 0) j = atomicAdd(counter, 1);
     return __shfl_sync(FULL, j, 0);
 }
+
+// B rows of one A row, for the CTA-per-row kernels that accumulate in GLOBAL memory (large rows).
+// Warps take B rows from a shared counter; a B row longer than LONG_B would keep one warp busy for
+// hundreds of dependent global-memory round trips (R-MAT hub columns: thousands of elements), so
+// it is listed and afterwards strided over by the whole CTA. f(j, p_first, p_end, p_stride)
+// handles the elements p_first, p_first + p_stride, ... < p_end of the B row of A entry j.
+// s_next / s_nlong must be zero on entry (and a barrier passed); all threads must call.
+constexpr int LONG_B = 256;
+constexpr int LONG_CAP = 96;
+template <typename F>
+__device__ __forceinline__ void cta_for_each_b_row(const int a0, const int a1, const int *__restrict__ colA,
+                                                   const int *__restrict__ rowptrB, int *s_next, int *s_nlong,
+                                                   int *s_long, F &&f)
+{
+    const int lane = threadIdx.x & 31;
+    for (int j = a0 + take_next(s_next, lane); j < a1; j = a0 + take_next(s_next, lane)) {
+        const int k = colA[j];
+        const int bs = rowptrB[k], be = rowptrB[k + 1];
+        if (be - bs > LONG_B) {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(s_nlong, 1);
+            idx = __shfl_sync(FULL, idx, 0);
+            if (idx < LONG_CAP) {
+                if (lane == 0) s_long[idx] = j;
+                continue;
+            }
+        }
+        f(j, bs + lane, be, 32);
+    }
+    __syncthreads();
+    const int nlong = min(*s_nlong, LONG_CAP);
+    for (int i = 0; i < nlong; ++i) {
+        const int j = s_long[i];
+        const int k = colA[j];
+        f(j, rowptrB[k] + (int)threadIdx.x, rowptrB[k + 1], (int)blockDim.x);
+    }
+}
+
 
 template <int LOG2T>
 __device__ __forceinline__ int table_insert(int *keys, int c, bool &is_new)

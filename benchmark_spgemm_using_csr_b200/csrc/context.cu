@@ -218,7 +218,7 @@ int reserve_workspace(bhb200_ctx *ctx)
 // per resident CTA, kept all-zero between uses
 int reserve_large_scratch(bhb200_ctx *ctx, bool need_prefix)
 {
-    const size_t nwords = ((size_t)ctx->n + 31) / 32;
+    const size_t nwords = (size_t)large_nwords(ctx->n);
     const size_t blocks = (size_t)large_scratch_blocks(ctx->sm_count);
     const size_t bytes = nwords * blocks * 4;
     if (bytes > ctx->bitmap.cap) ctx->bitmap_zeroed_bytes = 0;

@@ -461,7 +461,7 @@ k_num_large(const int *__restrict__ queue, const int count, const int *__restric
             int *__restrict__ prefix_all, const int nwords)
 {
     __shared__ int s_red[33];
-    __shared__ int s_lo, s_hi, s_next[2];
+    __shared__ int s_lo, s_hi, s_next[2], s_nlong[2], s_long[2][LONG_CAP];
     unsigned *bm = bitmap_all + (size_t)blockIdx.x * nwords;
     int *prefix = prefix_all + (size_t)blockIdx.x * nwords;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -471,6 +471,7 @@ k_num_large(const int *__restrict__ queue, const int count, const int *__restric
             s_lo = 0x7fffffff;
             s_hi = -1;
             s_next[0] = s_next[1] = 0;
+            s_nlong[0] = s_nlong[1] = 0;
         }
         __syncthreads();
         const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
@@ -478,17 +479,16 @@ k_num_large(const int *__restrict__ queue, const int count, const int *__restric
         const int nout = (int)(rowoff[row + 1] - o);
         // ---- 1. mark the row's columns; zero the row's values ----
         int wlo = 0x7fffffff, whi = -1;
-        for (int j = a0 + take_next(&s_next[0], lane); j < a1; j = a0 + take_next(&s_next[0], lane)) {
-            const int k = colA[j];
-            const int bs = rowptrB[k], be = rowptrB[k + 1];
-            for (int p = bs + lane; p < be; p += 32) {
-                const int c = colB[p];
-                const int w = c >> 5;
-                atomicOr(&bm[w], 1u << (c & 31));
-                wlo = min(wlo, w);
-                whi = max(whi, w);
-            }
-        }
+        cta_for_each_b_row(a0, a1, colA, rowptrB, &s_next[0], &s_nlong[0], s_long[0],
+                           [&](int, int p0, int pe, int stride) {
+                               for (int p = p0; p < pe; p += stride) {
+                                   const int c = colB[p];
+                                   const int w = c >> 5;
+                                   atomicOr(&bm[w], 1u << (c & 31));
+                                   wlo = min(wlo, w);
+                                   whi = max(whi, w);
+                               }
+                           });
         if (whi >= 0) {
             atomicMin(&s_lo, wlo);
             atomicMax(&s_hi, whi);
@@ -497,70 +497,90 @@ k_num_large(const int *__restrict__ queue, const int count, const int *__restric
         __threadfence();
         __syncthreads();
         // ---- 2. exclusive popcount prefix over the touched word range ----
-        const int lo = s_lo, hi = s_hi;
-        const int nw = hi - lo + 1;
-        const int per = (nw + (int)blockDim.x - 1) / (int)blockDim.x;
-        const int w0 = lo + (int)threadIdx.x * per;
-        const int w1 = min(w0 + per, hi + 1);
-        int mysum = 0;
-        for (int w = w0; w < w1; ++w) mysum += __popc(__ldcg(bm + w));
-        // block exclusive scan of mysum
-        {
-            int x = mysum;
+        // A warp owns a contiguous chunk of words and walks it 32 words at a time (coalesced;
+        // a chunk per THREAD made every load its own 32-byte sector: at n = 4 M columns this
+        // phase was most of the kernel's 28.6 ms in config 3).
+        // (16-byte loads, the next one issued before the current four words are processed.)
+        const int lo = s_lo & ~3, hi = s_hi | 3;   // whole uint4s; the bitmap is padded to 16 bytes
+        const int nq = (hi - lo + 1) >> 2;         // uint4s in the touched range
+        const uint4 *bq = reinterpret_cast<const uint4 *>(bm + lo);
+        const int chunk = (((nq + nwarps - 1) / nwarps) + 31) & ~31;
+        const int q0 = warp * chunk;
+        const int q1 = min(q0 + chunk, nq);
+        int wsum = 0;
+#pragma unroll 4
+        for (int qi = q0 + lane; qi < q1; qi += 32) {
+            const uint4 v = __ldcg(bq + qi);
+            wsum += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        }
+        wsum = warp_sum(wsum);
+        if (lane == 0) s_red[warp] = wsum;
+        __syncthreads();
+        if (warp == 0) {
+            int wv = (lane < nwarps) ? s_red[lane] : 0;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int y = __shfl_up_sync(FULL, x, d);
-                if (lane >= d) x += y;
+                const int y = __shfl_up_sync(FULL, wv, d);
+                if (lane >= d) wv += y;
             }
-            if (lane == 31) s_red[warp] = x;
-            __syncthreads();
-            if (warp == 0) {
-                int wv = (lane < nwarps) ? s_red[lane] : 0;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int y = __shfl_up_sync(FULL, wv, d);
-                    if (lane >= d) wv += y;
-                }
-                s_red[lane] = wv;
-            }
-            __syncthreads();
-            mysum = (warp ? s_red[warp - 1] : 0) + x - mysum;   // exclusive prefix of this thread
+            s_red[lane] = wv;
         }
-        int run = mysum;
-        for (int w = w0; w < w1; ++w) {
-            const unsigned bits = __ldcg(bm + w);
-            prefix[w] = run;
-            // columns of this word are final: write them now, in order
-            unsigned b = bits;
-            int r2 = run;
-            while (b) {
-                const int bit = __ffs(b) - 1;
-                b &= b - 1;
-                colC[o + r2] = (w << 5) | bit;
-                ++r2;
+        __syncthreads();
+        int run = warp ? s_red[warp - 1] : 0;   // outputs before this warp's chunk
+        uint4 nxt = (q0 + lane < q1) ? __ldcg(bq + q0 + lane) : make_uint4(0u, 0u, 0u, 0u);
+        for (int qb = q0; qb < q1; qb += 32) {
+            const uint4 v = nxt;
+            const int qn = qb + 32 + lane;
+            nxt = (qn < q1) ? __ldcg(bq + qn) : make_uint4(0u, 0u, 0u, 0u);
+            const int pc = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+            int incl = pc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += y;
             }
-            run += __popc(bits);
+            if (pc) {
+                int r2 = run + incl - pc;
+                const int wbase = lo + ((qb + lane) << 2);
+                const unsigned bits4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    unsigned b = bits4[u];
+                    if (b) prefix[wbase + u] = r2;   // (read back only for words that hold a column)
+                    // columns of this word are final: write them now, in order
+                    while (b) {
+                        const int bit = __ffs(b) - 1;
+                        b &= b - 1;
+                        colC[o + r2] = ((wbase + u) << 5) | bit;
+                        ++r2;
+                    }
+                }
+            }
+            run += __shfl_sync(FULL, incl, 31);
         }
         __threadfence();
         __syncthreads();
         // ---- 3. accumulate products at their rank ----
-        for (int j = a0 + take_next(&s_next[1], lane); j < a1; j = a0 + take_next(&s_next[1], lane)) {
-            const int k = colA[j];
-            const VT av = valA[j];
-            const int bs = rowptrB[k], be = rowptrB[k + 1];
-            for (int p = bs + lane; p < be; p += 32) {
-                const int c = colB[p];
-                const int w = c >> 5;
-                const unsigned bits = __ldcg(bm + w);
-                const int pos = __ldcg(prefix + w) + __popc(bits & ((1u << (c & 31)) - 1u));
-                atomicAdd(&valC[o + pos], av * valB[p]);
-            }
-        }
+        cta_for_each_b_row(a0, a1, colA, rowptrB, &s_next[1], &s_nlong[1], s_long[1],
+                           [&](int j, int p0, int pe, int stride) {
+                               const VT av = valA[j];
+                               // two elements per thread and step: their bitmap/prefix lookups overlap
+                               for (int p = p0; p < pe; p += 2 * stride) {
+                                   const int pb = p + stride;
+                                   const bool two = pb < pe;
+                                   const int ca = colB[p];
+                                   const int cb = two ? colB[pb] : ca;
+                                   const VT va = valB[p];
+                                   const VT vb = two ? valB[pb] : VT(0);
+                                   const unsigned bita = __ldcg(bm + (ca >> 5)), bitb = __ldcg(bm + (cb >> 5));
+                                   const int prea = __ldcg(prefix + (ca >> 5)), preb = __ldcg(prefix + (cb >> 5));
+                                   atomicAdd(&valC[o + prea + __popc(bita & ((1u << (ca & 31)) - 1u))], av * va);
+                                   if (two) atomicAdd(&valC[o + preb + __popc(bitb & ((1u << (cb & 31)) - 1u))], av * vb);
+                               }
+                           });
         __syncthreads();
-        // ---- 4. restore the all-zero bitmap ----
-        for (int w = lo + (int)threadIdx.x; w <= hi; w += blockDim.x) {
-            if (__ldcg(bm + w)) bm[w] = 0u;
-        }
+        // ---- 4. restore the all-zero bitmap: only the words of the row's output columns ----
+        for (int i = threadIdx.x; i < nout; i += blockDim.x) bm[colC[o + i] >> 5] = 0u;
         __threadfence();
         __syncthreads();
     }
@@ -653,7 +673,7 @@ static cudaError_t launch_num_large_t(const LaunchCtx &lc, const int *queue, int
                                       int *prefix_scratch, int scratch_blocks)
 {
     if (count <= 0) return cudaSuccess;
-    const int nwords = (n + 31) / 32;
+    const int nwords = large_nwords(n);
     const int blocks = count < scratch_blocks ? count : scratch_blocks;
     ++*lc.launches;
     k_num_large<VT><<<blocks, 1024, 0, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,

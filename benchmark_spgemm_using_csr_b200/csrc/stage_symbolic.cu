@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(1024) k_sym_large(const int *__restrict__ queu
                                                     const int nwords)
 {
     __shared__ int s_red[33];
-    __shared__ int s_lo, s_hi, s_next;
+    __shared__ int s_lo, s_hi, s_next, s_nlong, s_long[LONG_CAP];
     unsigned *bm = bitmap_all + (size_t)blockIdx.x * nwords;
     const int lane = threadIdx.x & 31;
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
@@ -135,21 +135,20 @@ __global__ void __launch_bounds__(1024) k_sym_large(const int *__restrict__ queu
             s_lo = 0x7fffffff;
             s_hi = -1;
             s_next = 0;
+            s_nlong = 0;
         }
         __syncthreads();
         const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
         int wlo = 0x7fffffff, whi = -1;
-        for (int j = a0 + take_next(&s_next, lane); j < a1; j = a0 + take_next(&s_next, lane)) {
-            const int k = colA[j];
-            const int bs = rowptrB[k], be = rowptrB[k + 1];
-            for (int p = bs + lane; p < be; p += 32) {
+        cta_for_each_b_row(a0, a1, colA, rowptrB, &s_next, &s_nlong, s_long, [&](int, int p0, int pe, int stride) {
+            for (int p = p0; p < pe; p += stride) {
                 const int c = colB[p];
                 const int w = c >> 5;
                 atomicOr(&bm[w], 1u << (c & 31));
                 wlo = min(wlo, w);
                 whi = max(whi, w);
             }
-        }
+        });
         if (whi >= 0) {
             atomicMin(&s_lo, wlo);
             atomicMax(&s_hi, whi);
@@ -259,7 +258,7 @@ cudaError_t launch_sym_large(const LaunchCtx &lc, const int *queue, int count, i
                              unsigned *bitmap_scratch, int scratch_blocks)
 {
     if (count <= 0) return cudaSuccess;
-    const int nwords = (n + 31) / 32;
+    const int nwords = large_nwords(n);
     int blocks = count < scratch_blocks ? count : scratch_blocks;
     ++*lc.launches;
     k_sym_large<<<blocks, 1024, 0, lc.stream>>>(queue, count, A.rowptr, A.col, B.rowptr, B.col, rc, bitmap_scratch, nwords);
