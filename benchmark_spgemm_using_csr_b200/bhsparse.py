@@ -125,6 +125,22 @@ class bhsparse:
         return self._lib.bhb200_free_mem(self._ctx) if self._ctx else BHSPARSE_SUCCESS
 
     # -- additions (no reference counterpart) --------------------------------------
+    def update_values(self, csrValA=None, csrValB=None) -> int:
+        """New values for A and/or B, same patterns (include/bhsparse_b200.h: bhb200_update_values_*)."""
+        if not self._ctx:
+            return capi.ERR_INVALID
+        for v in (csrValA, csrValB):
+            if v is not None and (v.dtype != self._dtype or not v.flags.c_contiguous):
+                return capi.ERR_INVALID
+        fn = self._lib.bhb200_update_values_f64 if self._dtype == np.float64 else self._lib.bhb200_update_values_f32
+        ap = ctypes.c_void_p(csrValA.ctypes.data) if csrValA is not None else None
+        bp = ctypes.c_void_p(csrValB.ctypes.data) if csrValB is not None else None
+        return fn(self._ctx, ap, bp)
+
+    def spgemm_numeric(self) -> int:
+        """Values of C again after update_values; structure of C reused (bhb200_spgemm_numeric)."""
+        return self._lib.bhb200_spgemm_numeric(self._ctx) if self._ctx else capi.ERR_INVALID
+
     def get_rowptrC_i64(self) -> np.ndarray:
         out = np.empty(self._m + 1, dtype=np.int64)
         capi.check(self._lib, self._ctx, self._lib.bhb200_get_rowptrC_i64(self._ctx, ctypes.c_void_p(out.ctypes.data)))

@@ -35,6 +35,7 @@ EXPORTED = [
     "bhb200_warmup", "bhb200_spgemm", "bhb200_synchronize", "bhb200_get_nnzC", "bhb200_get_C_f64",
     "bhb200_get_C_f32", "bhb200_get_rowptrC_i64", "bhb200_get_C_device", "bhb200_copy_C_to_device", "bhb200_get_row_products",
     "bhb200_get_stats", "bhb200_set_profiling", "bhb200_free_mem", "bhb200_version",
+    "bhb200_update_values_f64", "bhb200_update_values_f32", "bhb200_spgemm_numeric",
 ]
 
 
@@ -104,6 +105,9 @@ def load(build_if_missing: bool = False):
     L.bhb200_warmup.argtypes = [ctxp]
     L.bhb200_spgemm.argtypes = [ctxp]
     L.bhb200_synchronize.argtypes = [ctxp]
+    L.bhb200_update_values_f64.argtypes = [ctxp, c_void_p, c_void_p]
+    L.bhb200_update_values_f32.argtypes = [ctxp, c_void_p, c_void_p]
+    L.bhb200_spgemm_numeric.argtypes = [ctxp]
     L.bhb200_get_nnzC.argtypes = [ctxp]
     L.bhb200_get_nnzC.restype = c_int64
     L.bhb200_get_C_f64.argtypes = [ctxp, c_void_p, c_void_p, c_void_p]

@@ -87,6 +87,11 @@ struct bhb200_ctx {
 
     bool have_C = false;
     int64_t nnzC = 0;
+    // structure reuse (bhb200_spgemm_numeric): what the last full product left behind
+    int last_G = 32;
+    WordLists last_wl{nullptr, nullptr, nullptr, nullptr, 0};
+    bool reuse_bins_valid = false;   // queue holds the numeric bins without the copy bin
+    int reuse_num_bin[MAX_BINS] = {0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timing_valid = false;
     bool profiling = false;
@@ -280,6 +285,68 @@ void offsets_from_counts(const int *counts, BinOffsets &o)
     o.off[MAX_BINS] = acc;
 }
 
+// Numeric kernels of every bin except the Ct -> C copy; shared by bhb200_spgemm (stage 4) and
+// bhb200_spgemm_numeric (values only, structure of C reused).
+int run_numeric_bins(bhb200_ctx *ctx, const LaunchCtx &lc, const int *num_bin, const BinOffsets &no, int G,
+                     const WordLists &wl)
+{
+    int rc = 0;
+    int *queue = ctx->queue.as<int>();
+    int64_t *rowoff = ctx->rowoff64.as<int64_t>();
+    int *rlo = ctx->rlo.as<int>();
+    int *colC = ctx->colC.as<int>();
+    void *valC = ctx->valC.p;
+    if (num_bin[NB_ONE] > 0) CU(stamp(ctx, 1, NB_ONE), "event");
+    CU(launch_num_single(lc, ctx->dtype, queue + no.off[NB_ONE], num_bin[NB_ONE], ctx->A, ctx->B, rowoff, colC, valC),
+       "numeric single");
+    if (num_bin[NB_ESC] > 0) CU(stamp(ctx, 1, NB_ESC), "event");
+    CU(launch_num_esc(lc, ctx->dtype, queue + no.off[NB_ESC], num_bin[NB_ESC], ctx->n, ctx->A, ctx->B, rowoff, colC, valC),
+       "numeric ESC");
+    for (int b = NB_G64; b <= NB_B16384; ++b) {
+        if (num_bin[b] > 0) CU(stamp(ctx, 1, b), "event");
+        if (ctx->dtype == BHB200_DTYPE_F64)
+            CU(launch_num_hash_f64(lc, b, G, queue + no.off[b], num_bin[b], ctx->A, ctx->B, rowoff, colC, (double *)valC),
+               "numeric hash f64");
+        else
+            CU(launch_num_hash_f32(lc, b, G, queue + no.off[b], num_bin[b], ctx->A, ctx->B, rowoff, colC, (float *)valC),
+               "numeric hash f32");
+    }
+    if (num_bin[NB_LARGE] > 0) {
+        rc = reserve_large_scratch(ctx, true);
+        if (rc) return rc;
+        const int sb = large_scratch_blocks(ctx->sm_count);
+        CU(stamp(ctx, 1, NB_LARGE), "event");
+        if (ctx->dtype == BHB200_DTYPE_F64)
+            CU(launch_num_large_f64(lc, queue + no.off[NB_LARGE], num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
+                                    (double *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
+               "numeric large f64");
+        else
+            CU(launch_num_large_f32(lc, queue + no.off[NB_LARGE], num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
+                                    (float *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
+               "numeric large f32");
+    }
+    {
+        const int rb[4] = {NB_RANGE_S128, NB_RANGE_S512, NB_RANGE_L128, NB_RANGE_L512};
+        const int rnsum[4] = {NSUM_SMALL, NSUM_SMALL, NSUM_LARGE, NSUM_LARGE};
+        const int rnacc[4] = {128, RANGE_NACC_MAX, 128, RANGE_NACC_MAX};
+        for (int i = 0; i < 4; ++i) {
+            const int b = rb[i];
+            if (num_bin[b] <= 0) continue;
+            CU(stamp(ctx, 1, b), "event");
+            if (ctx->dtype == BHB200_DTYPE_F64)
+                CU(launch_num_range_f64(lc, rnsum[i], rnacc[i], queue + no.off[b], num_bin[b], ctx->A, ctx->B, rlo, rowoff,
+                                        colC, (double *)valC, wl),
+                   "numeric range f64");
+            else
+                CU(launch_num_range_f32(lc, rnsum[i], rnacc[i], queue + no.off[b], num_bin[b], ctx->A, ctx->B, rlo, rowoff,
+                                        colC, (float *)valC, wl),
+                   "numeric range f32");
+        }
+    }
+    return BHB200_SUCCESS;
+}
+
+
 }  // namespace
 
 // ============================================================================
@@ -457,6 +524,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     if (!ctx || !ctx->have_data) return fail(ctx, BHB200_ERR_INVALID, "spgemm before initData");
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     ctx->have_C = false;
+    ctx->reuse_bins_valid = false;
     ctx->timing_valid = false;
     ctx->launches = 0;
     bhb200_stats &st = ctx->stats;
@@ -687,55 +755,10 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(cudaEventRecord(ctx->ev[3], s), "event");
 
     // ---- stage 4: numeric, C written in place ----
+    rc = run_numeric_bins(ctx, lc, hc.num_bin, no, G, wl);
+    if (rc) return rc;
     int *colC = ctx->colC.as<int>();
     void *valC = ctx->valC.p;
-    if (hc.num_bin[NB_ONE] > 0) CU(stamp(ctx, 1, NB_ONE), "event");
-    CU(launch_num_single(lc, ctx->dtype, queue + no.off[NB_ONE], hc.num_bin[NB_ONE], ctx->A, ctx->B, rowoff, colC, valC),
-       "numeric single");
-    if (hc.num_bin[NB_ESC] > 0) CU(stamp(ctx, 1, NB_ESC), "event");
-    CU(launch_num_esc(lc, ctx->dtype, queue + no.off[NB_ESC], hc.num_bin[NB_ESC], ctx->n, ctx->A, ctx->B, rowoff, colC, valC),
-       "numeric ESC");
-    for (int b = NB_G64; b <= NB_B16384; ++b) {
-        if (hc.num_bin[b] > 0) CU(stamp(ctx, 1, b), "event");
-        if (ctx->dtype == BHB200_DTYPE_F64)
-            CU(launch_num_hash_f64(lc, b, G, queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rowoff, colC, (double *)valC),
-               "numeric hash f64");
-        else
-            CU(launch_num_hash_f32(lc, b, G, queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rowoff, colC, (float *)valC),
-               "numeric hash f32");
-    }
-    if (hc.num_bin[NB_LARGE] > 0) {
-        rc = reserve_large_scratch(ctx, true);
-        if (rc) return rc;
-        const int sb = large_scratch_blocks(ctx->sm_count);
-        CU(stamp(ctx, 1, NB_LARGE), "event");
-        if (ctx->dtype == BHB200_DTYPE_F64)
-            CU(launch_num_large_f64(lc, queue + no.off[NB_LARGE], hc.num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
-                                    (double *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
-               "numeric large f64");
-        else
-            CU(launch_num_large_f32(lc, queue + no.off[NB_LARGE], hc.num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
-                                    (float *)valC, ctx->bitmap.as<unsigned>(), ctx->prefix.as<int>(), sb),
-               "numeric large f32");
-    }
-    {
-        const int rb[4] = {NB_RANGE_S128, NB_RANGE_S512, NB_RANGE_L128, NB_RANGE_L512};
-        const int rnsum[4] = {NSUM_SMALL, NSUM_SMALL, NSUM_LARGE, NSUM_LARGE};
-        const int rnacc[4] = {128, RANGE_NACC_MAX, 128, RANGE_NACC_MAX};
-        for (int i = 0; i < 4; ++i) {
-            const int b = rb[i];
-            if (hc.num_bin[b] <= 0) continue;
-            CU(stamp(ctx, 1, b), "event");
-            if (ctx->dtype == BHB200_DTYPE_F64)
-                CU(launch_num_range_f64(lc, rnsum[i], rnacc[i], queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rlo, rowoff,
-                                        colC, (double *)valC, wl),
-                   "numeric range f64");
-            else
-                CU(launch_num_range_f32(lc, rnsum[i], rnacc[i], queue + no.off[b], hc.num_bin[b], ctx->A, ctx->B, rlo, rowoff,
-                                        colC, (float *)valC, wl),
-                   "numeric range f32");
-        }
-    }
     if (hc.num_bin[NB_COPY] > 0) {
         CU(stamp(ctx, 1, NB_COPY), "event");
         CU(launch_copy_ct(lc, ctx->dtype, queue + no.off[NB_COPY], hc.num_bin[NB_COPY], rowoff, ctx->ct_off.as<long long>(),
@@ -753,9 +776,87 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     st.bytes_compulsory = (m1 * 4 + (int64_t)ctx->nnzA * (4 + v)) + (((int64_t)ctx->k + 1) * 4 + (int64_t)ctx->nnzB * (4 + v)) +
                           (m1 * 4 + ctx->nnzC * (4 + v));
     st.workspace_bytes = (int64_t)ctx->dev_bytes;
+    ctx->last_G = G;
+    ctx->last_wl = wl;
     ctx->have_C = true;
     ctx->timing_valid = true;
     return BHB200_SUCCESS;
+}
+
+// Values of C for new values of A and/or B with the SAME sparsity patterns as the last
+// bhb200_spgemm: stage 1, the symbolic pass, the scan and the allocation are skipped; the
+// numeric kernels run on the known row sizes and overwrite C in place (AMG
+// set-up phases multiply the same patterns many times).
+int bhb200_spgemm_numeric(bhb200_ctx *ctx)
+{
+    if (!ctx || !ctx->have_data || !ctx->have_C)
+        return fail(ctx, BHB200_ERR_INVALID, "spgemm_numeric needs a completed spgemm on the same operands");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ctx->timing_valid = false;
+    ctx->launches = 0;
+    bhb200_stats &st = ctx->stats;
+    cudaStream_t s = ctx->stream;
+    LaunchCtx lc{s, ctx->sm_count, &ctx->launches, ctx->max_span};
+    Counters *d_ctr = ctx->counters.as<Counters>();
+    CU(cudaEventRecord(ctx->ev[0], s), "event");
+    CU(cudaEventRecord(ctx->ev[1], s), "event");
+    CU(cudaEventRecord(ctx->ev[2], s), "event");
+    memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
+    if (!ctx->reuse_bins_valid) {
+        // numeric bins of ALL rows (the direct-mode rows of the full product sit in the copy bin)
+        CU(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s), "zero counters");
+        CU(launch_scan(lc, ctx->m, ctx->A.rowptr, ctx->prod.as<int>(), ctx->rc.as<int>(), ctx->rspan.as<int>(), 0u, nullptr,
+                       ctx->rowoff64.as<int64_t>(), ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
+           "row pointer scan");
+        CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
+        CU(cudaStreamSynchronize(s), "numeric-only binning");
+        if ((int64_t)ctx->h_ctr->nnzC != ctx->nnzC) return fail(ctx, BHB200_ERR_INVALID, "structure of C changed");
+        memcpy(ctx->reuse_num_bin, ctx->h_ctr->num_bin, sizeof(ctx->reuse_num_bin));
+        BinOffsets no0;
+        offsets_from_counts(ctx->reuse_num_bin, no0);
+        CU(launch_bin_scatter(lc, true, ctx->m, ctx->prod.as<int>(), ctx->rc.as<int>(), ctx->rspan.as<int>(), 0u, nullptr, no0,
+                              d_ctr, ctx->queue.as<int>()),
+           "numeric bin scatter");
+        ctx->reuse_bins_valid = true;
+    }
+    BinOffsets no;
+    offsets_from_counts(ctx->reuse_num_bin, no);
+    CU(cudaEventRecord(ctx->ev[3], s), "event");
+    int rc = run_numeric_bins(ctx, lc, ctx->reuse_num_bin, no, ctx->last_G, ctx->last_wl);
+    if (rc) return rc;
+    CU(stamp(ctx, 1, MAX_BINS), "event");
+    CU(cudaEventRecord(ctx->ev[4], s), "event");
+    for (int b = 0; b < BHB200_NUM_NUM_BINS && b < MAX_BINS; ++b) st.num_bin_rows[b] = ctx->reuse_num_bin[b];
+    st.kernel_launches = ctx->launches;
+    st.direct_rows = 0;
+    st.direct_retry_rows = 0;
+    ctx->timing_valid = true;
+    return BHB200_SUCCESS;
+}
+
+static int update_values_any(bhb200_ctx *ctx, int dtype, const void *valA, const void *valB)
+{
+    if (!ctx || !ctx->have_data) return fail(ctx, BHB200_ERR_INVALID, "update_values before initData");
+    if (ctx->borrowed) return fail(ctx, BHB200_ERR_INVALID, "operands are caller-owned device arrays: update them in place");
+    if (dtype != ctx->dtype) return fail(ctx, BHB200_ERR_INVALID, "value type differs from initData");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t vs = vsize(ctx->dtype);
+    if (valA && ctx->nnzA > 0)
+        CU(cudaMemcpyAsync(ctx->a_val.p, valA, (size_t)ctx->nnzA * vs, cudaMemcpyHostToDevice, ctx->stream), "H2D valA");
+    if (valB && ctx->nnzB > 0)
+        CU(cudaMemcpyAsync(ctx->b_val.p, valB, (size_t)ctx->nnzB * vs, cudaMemcpyHostToDevice, ctx->stream), "H2D valB");
+    CU(cudaStreamSynchronize(ctx->stream), "update values");
+    return BHB200_SUCCESS;
+}
+
+int bhb200_update_values_f64(bhb200_ctx *ctx, const double *valA, const double *valB)
+{
+    return update_values_any(ctx, BHB200_DTYPE_F64, valA, valB);
+}
+
+int bhb200_update_values_f32(bhb200_ctx *ctx, const float *valA, const float *valB)
+{
+    return update_values_any(ctx, BHB200_DTYPE_F32, valA, valB);
 }
 
 int bhb200_set_profiling(bhb200_ctx *ctx, int enabled)

@@ -106,6 +106,18 @@ public:
         return (c < 0 || c > 0x7fffffffLL) ? -1 : (int)c;
     }
 
+    /* Additions (no reference counterpart): new values, same patterns -> values of C only. */
+    int update_values(const value_type *csrValA, const value_type *csrValB)
+    {
+        if (!_ctx) return BHB200_ERR_INVALID;
+#ifdef BHSPARSE_VALUE_FLOAT
+        return bhb200_update_values_f32(_ctx, csrValA, csrValB);
+#else
+        return bhb200_update_values_f64(_ctx, csrValA, csrValB);
+#endif
+    }
+    int spgemm_numeric() { return _ctx ? bhb200_spgemm_numeric(_ctx) : BHB200_ERR_INVALID; }
+
     int get_C(index_type *csrColIndC, value_type *csrValC)   /* bhsparse_cuda.h:3011-3020 */
     {
         if (!_ctx) return BHB200_ERR_INVALID;

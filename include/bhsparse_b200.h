@@ -126,6 +126,22 @@ BHB200_API int bhb200_warmup(bhb200_ctx *ctx);
 BHB200_API int bhb200_spgemm(bhb200_ctx *ctx);
 BHB200_API int bhb200_synchronize(bhb200_ctx *ctx);
 
+/* -- repeated products with the same patterns (no reference
+ * counterpart: the reference recomputes everything, bhsparse.h:260-339) --------
+ * bhb200_update_values_* replaces the VALUES of A and/or B (host arrays of nnzA /
+ * nnzB entries; NULL keeps the current ones); row pointers and column indices
+ * stay those of the last bhb200_init_data_*.  With bhb200_init_data_device the
+ * caller owns the device arrays and simply overwrites them (the call returns
+ * BHB200_ERR_INVALID).
+ * bhb200_spgemm_numeric recomputes the values of C after a completed
+ * bhb200_spgemm on the same operands: row pointers and column indices of C are
+ * kept, the upper-bound, symbolic, scan and allocation stages are skipped, the
+ * numeric kernels overwrite the values in place.  Returns BHB200_ERR_INVALID if
+ * there is no completed product to reuse. */
+BHB200_API int bhb200_update_values_f64(bhb200_ctx *ctx, const double *valA, const double *valB);
+BHB200_API int bhb200_update_values_f32(bhb200_ctx *ctx, const float *valA, const float *valB);
+BHB200_API int bhb200_spgemm_numeric(bhb200_ctx *ctx);
+
 /* -- results -------------------------------------------------------------------
  * bhb200_get_nnzC replaces bhsparse::get_nnzC (bhsparse_cuda.h:3006-3009) with
  * a 64-bit count.  bhb200_get_C_{f64,f32} replace bhsparse::get_C
