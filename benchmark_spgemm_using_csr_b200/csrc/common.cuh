@@ -594,7 +594,8 @@ cudaError_t launch_num_large_f32(const LaunchCtx &lc, const int *queue, int coun
 cudaError_t launch_num_large_f64(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B,
                                  const int64_t *rowoff, int *colC, double *valC, unsigned *bitmap_scratch,
                                  int *prefix_scratch, int scratch_blocks);
-int large_scratch_blocks(int sm_count);
+// resident CTAs (= private scratch sets) of the large-row kernels for n columns
+int large_scratch_blocks(int sm_count, int n);
 // stage_range.cu (symbolic) / stage_numeric (numeric) -- shared-memory bitmap kernels
 // (the launchers pick the 128-bit vectorised kernels of stage_range_vec.cuh when B is 16-byte aligned)
 cudaError_t launch_sym_range(const LaunchCtx &lc, int nsum, const int *queue, int count, Csr A, Csr B, const int *rlo,

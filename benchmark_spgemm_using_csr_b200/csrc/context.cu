@@ -224,7 +224,7 @@ int reserve_workspace(bhb200_ctx *ctx)
 int reserve_large_scratch(bhb200_ctx *ctx, bool need_prefix)
 {
     const size_t nwords = (size_t)large_nwords(ctx->n);
-    const size_t blocks = (size_t)large_scratch_blocks(ctx->sm_count);
+    const size_t blocks = (size_t)large_scratch_blocks(ctx->sm_count, ctx->n);
     const size_t bytes = nwords * blocks * 4;
     if (bytes > ctx->bitmap.cap) ctx->bitmap_zeroed_bytes = 0;
     CU(ctx->bitmap.reserve(bytes, &ctx->dev_bytes), "alloc bitmap scratch");
@@ -314,7 +314,7 @@ int run_numeric_bins(bhb200_ctx *ctx, const LaunchCtx &lc, const int *num_bin, c
     if (num_bin[NB_LARGE] > 0) {
         rc = reserve_large_scratch(ctx, true);
         if (rc) return rc;
-        const int sb = large_scratch_blocks(ctx->sm_count);
+        const int sb = large_scratch_blocks(ctx->sm_count, ctx->n);
         CU(stamp(ctx, 1, NB_LARGE), "event");
         if (ctx->dtype == BHB200_DTYPE_F64)
             CU(launch_num_large_f64(lc, queue + no.off[NB_LARGE], num_bin[NB_LARGE], ctx->n, ctx->A, ctx->B, rowoff, colC,
@@ -708,7 +708,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         if (rc) return rc;
         CU(stamp(ctx, 0, SB_LARGE), "event");
         CU(launch_sym_large(lc, queue + so.off[SB_LARGE], hc.sym_bin[SB_LARGE], ctx->n, ctx->A, ctx->B, rcnt,
-                            ctx->bitmap.as<unsigned>(), large_scratch_blocks(ctx->sm_count)),
+                            ctx->bitmap.as<unsigned>(), large_scratch_blocks(ctx->sm_count, ctx->n)),
            "symbolic large");
     }
     WordLists wl{nullptr, nullptr, nullptr, nullptr, 0};
