@@ -330,25 +330,6 @@ __device__ __forceinline__ void bitonic_sort_smem_group(int *sk, const int N, co
         }
     }
 }
-// Same by a whole block.
-__device__ __forceinline__ void bitonic_sort_smem_block(int *sk, const int N)
-{
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const int a = sk[i], b = sk[p];
-                const bool asc = (i & k) == 0;
-                if ((a > b) == asc) {
-                    sk[i] = b;
-                    sk[p] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
 
 // Same network with the stage loops rolled (only the per-key work is unrolled): for R >= 16
 // the fully unrolled version is 30-70 KB of straight-line code and thrashes the
