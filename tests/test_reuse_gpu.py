@@ -88,3 +88,21 @@ def test_update_values_rejects_borrowed_and_wrong_type():
     assert bh.update_values(A.val.astype(np.float32), None) == capi.ERR_INVALID
     assert bh.update_values(None, None) == BHSPARSE_SUCCESS
     bh.freePlatform()
+
+
+def test_reuse_empty_product():
+    """A without entries: the numeric-only call must succeed and leave an empty C."""
+    A = gen.CSR(5, 7, np.zeros(6, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0))
+    B = gen.poisson5pt(7, 1)
+    platforms = [False] * NUM_PLATFORMS
+    platforms[BHSPARSE_CUDA] = True
+    bh = bhsparse()
+    bh.initPlatform(platforms)
+    rowptrC = np.full(6, -1, dtype=np.int32)
+    assert bh.initData(5, 7, 7, 0, A.val, A.rowptr, A.col, B.nnz, B.val, B.rowptr, B.col, rowptrC) == BHSPARSE_SUCCESS
+    assert bh.spgemm() == BHSPARSE_SUCCESS and bh.get_nnzC() == 0
+    assert bh.update_values(None, B.val * 2) == BHSPARSE_SUCCESS
+    assert bh.spgemm_numeric() == BHSPARSE_SUCCESS and bh.get_nnzC() == 0
+    assert bh.get_C(np.empty(0, dtype=np.int32), np.empty(0)) == BHSPARSE_SUCCESS
+    assert np.array_equal(rowptrC, np.zeros(6, dtype=np.int32))
+    bh.freePlatform()
