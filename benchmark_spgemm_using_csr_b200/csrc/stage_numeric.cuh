@@ -8,10 +8,13 @@
 //      warp shuffles; R==0: bitonic in shared memory), look each sorted column's value up
 //      again and store the row at rowptrC[row] with coalesced writes.
 //      Covers what ESC_bitonic_scan (bhsparse_cuda.h:1400-1518) and the first rounds of
-//      EM_mergepath (:1902-2157) do in the reference, for nnz(C_i) <= 1024.
-// k_num_block<VT,LOG2T>     : one CTA per row, nnz(C_i) <= 8192, same scheme with a CTA-wide
-//      table (up to 224 KB of shared memory) -- the rows the reference sends through
-//      EM_mergepath rounds 2..5 and EM_mergepath_global (:2270-2525).
+//      EM_mergepath (:1902-2157) do in the reference; used for nnz(C_i) <= 256.
+// k_num_direct<VT,G,LOG2T,R[,FILTER]> : the same kernel as a single pass (no symbolic pass before
+//      it): rows are staged `cap` entries apart and copied to their place by k_copy_ct.
+// k_num_block<VT,LOG2T,THREADS[,DIRECT]> : one CTA per row, 256 < nnz(C_i) <= 8192, a CTA-wide
+//      table (up to 224 KB of shared memory), B rows taken dynamically by the warps, CTA-wide
+//      register sort -- the rows the reference sends through EM_mergepath rounds 2..5 and
+//      EM_mergepath_global (:2270-2525). DIRECT: single-pass variant for bins that barely compress.
 // k_num_large<VT>           : longer rows: rank of a column = popcount prefix of the row's
 //      column bitmap (global, L2 resident); products are accumulated straight into the
 //      final C row with red.global.add -- no spill, no re-allocation, no sort.

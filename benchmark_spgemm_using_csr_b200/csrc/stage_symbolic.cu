@@ -3,7 +3,8 @@
 // k_sym_group<G,LOG2T> : a group of G lanes (8 or 32) owns a row and a T-slot column
 //                        table in shared memory; B rows are streamed one per step with
 //                        coalesced loads of their column segments.
-// k_sym_block<LOG2T>   : one CTA per row, up to 32768 slots (128 KB) -- the sizes for which
+//                        (tables up to 1024 slots; larger ones only for sampling and retries).
+// k_sym_block<LOG2T>   : one CTA per row, 2048 to 32768 slots (128 KB) -- the sizes for which
 //                        the reference needs its iterative merge with host re-allocation
 //                        (EM_mergepath, bhsparse_cuda.h:1902-2157, host loop :2527-2780).
 // k_sym_large          : rows beyond that: column bitmap in global memory (L2 resident).
