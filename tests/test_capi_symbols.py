@@ -54,3 +54,31 @@ def test_no_cpu_fallback_without_gpu():
     A = gen.poisson5pt(4, 4)
     with pytest.raises(capi.BhsparseError):
         spgemm(A, A)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 and a C caller must link
+    against the shared library (no compute call: there is no GPU here)."""
+    import shutil
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not cc:
+        pytest.skip("no C compiler")
+    capi.load(build_if_missing=True)
+    src = tmp_path / "caller.c"
+    src.write_text('#include <stdio.h>\n#include "bhsparse_b200.h"\n'
+                   'int main(void) {\n'
+                   '    bhb200_ctx *ctx = NULL;\n'
+                   '    printf("%s\\n", bhb200_version());\n'
+                   '    int rc = bhb200_create(&ctx, 0);\n'
+                   '    if (rc == BHB200_SUCCESS) bhb200_destroy(ctx);\n'
+                   '    return (rc == BHB200_SUCCESS || rc == BHB200_ERR_NO_DEVICE) ? 0 : 1;\n'
+                   '}\n')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-lbhsparse_b200", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "sm_100a" in r.stdout, (r.stdout, r.stderr)
