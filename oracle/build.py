@@ -3,13 +3,7 @@
 `python -m oracle.build` compiles oracle/spgemm_oracle.c into
 oracle/liboracle_spgemm.so with gcc + OpenMP.
 
-oracle/_ref/ (the real reference, compiled) is NOT produced: the reference's
-only CPU-side code for this path, SpGEMM_cuda/ref_spgemm.h, needs the CUSP
-headers (ref_spgemm.h:15-17; cusp::multiply at :73), which are neither vendored
-in /root/reference nor installed here, and its GPU kernels use the pre-Volta
-`__shfl_up` intrinsics (bhsparse_cuda.h:1031,1081,1133) that nvcc rejects for
-sm_100a.  So the reference is "unbuildable" in the sense of the task rules and
-the oracle is pinned by known-answer vectors instead (see spgemm_oracle.c).
+oracle/_ref/ (the reference itself, compiled for sm_100a) is built by oracle/build_ref.py.
 """
 import os
 import shutil

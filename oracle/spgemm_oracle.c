@@ -6,14 +6,15 @@
  * in __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs may
  * load it.  The product path (benchmark_spgemm_using_csr_b200) never calls it.
  *
- * PARITY STATUS: "parity unpinned" by reference-run outputs.  The reference's own
- * check (SpGEMM_cuda/ref_spgemm.h:65-127) calls cusp::multiply (CUSP v0.4.0,
- * README.md:91), an un-vendored third-party dependency that is absent from
- * /root/reference, and the reference stores no expected outputs.  This oracle
- * is therefore pinned against (i) the hand-derived result of the reference's
- * only deterministic known-answer case, test_small_spgemm (main.cu:149-246),
- * (ii) cage4.mtx squared (the shipped fixture) and (iii) scipy.sparse as a
- * second opinion on positive-valued inputs -- see tests/test_oracle.py.
+ * PARITY STATUS: PINNED by outputs of the reference itself.  The reference's own check
+ * (SpGEMM_cuda/ref_spgemm.h:65-127) calls cusp::multiply (CUSP v0.4.0, README.md:91), an
+ * un-vendored dependency, and stores no expected outputs -- but its GPU path compiles:
+ * oracle/build_ref.py builds bhsparse.h + bhsparse_cuda.h for sm_100a (oracle/_ref), and
+ * tests/golden/ref_outputs.npz holds what it produced on a B200 for the 18 x 2 cases of
+ * tests/ref_cases.py (tests/golden/make_ref_golden.py).  tests/test_oracle_pinned.py checks
+ * this oracle against those vectors on the CPU; tests/test_reference_gpu.py re-runs the
+ * reference live beside the library.  Also pinned by the hand-derived result of
+ * test_small_spgemm (main.cu:149-246), cage4.mtx squared and scipy.sparse (tests/test_oracle.py).
  *
  * What it restates (all citations relative to /root/reference/SpGEMM_cuda):
  *  - the result contract checked by ref_spgemm::compData (ref_spgemm.h:79-126):
