@@ -96,6 +96,10 @@ class bhsparse:
         if not self._ctx:
             return capi.ERR_INVALID
         err = self._lib.bhb200_spgemm(self._ctx)
+        # create_C leaves rowptrC in the caller's array at the end of spgemm() (bhsparse_cuda.h:2787-2808)
+        if err == BHSPARSE_SUCCESS and self._rowptrC is not None and 0 <= self.get_nnzC() <= 0x7fffffff:
+            fn = self._lib.bhb200_get_C_f64 if self._dtype == np.float64 else self._lib.bhb200_get_C_f32
+            err = fn(self._ctx, ctypes.c_void_p(self._rowptrC.ctypes.data), None, None)
         if err == BHSPARSE_SUCCESS and self._verbose:
             st = self.stats()
             t = st["ms_total"]
@@ -146,6 +150,14 @@ class bhsparse:
         capi.check(self._lib, self._ctx, self._lib.bhb200_get_rowptrC_i64(self._ctx, ctypes.c_void_p(out.ctypes.data)))
         return out
 
+    def get_C_range(self, first: int, count: int):
+        """Entries [first, first+count) of (colC, valC): piecewise access for results beyond INT32_MAX."""
+        col = np.empty(max(count, 0), dtype=np.int32)
+        val = np.empty(max(count, 0), dtype=self._dtype)
+        capi.check(self._lib, self._ctx, self._lib.bhb200_get_C_range(
+            self._ctx, int(first), int(count), ctypes.c_void_p(col.ctypes.data), ctypes.c_void_p(val.ctypes.data)))
+        return col, val
+
     def get_row_products(self) -> np.ndarray:
         out = np.empty(max(self._m, 1), dtype=np.int32)
         capi.check(self._lib, self._ctx, self._lib.bhb200_get_row_products(self._ctx, ctypes.c_void_p(out.ctypes.data)))
@@ -167,7 +179,7 @@ class bhsparse:
             pass
 
 
-def spgemm(A, B, device: int = 0, return_stats: bool = False):
+def spgemm(A, B, device: int = 0, return_stats: bool = False, return_row_products: bool = False):
     """Convenience driver following main.cu:104-135: C = A*B for two
     generators.CSR operands; returns (rowptrC int32, colC int32, valC)."""
     platforms = [False] * NUM_PLATFORMS
@@ -190,6 +202,12 @@ def spgemm(A, B, device: int = 0, return_stats: bool = False):
     valC = np.empty(max(nnzC, 0), dtype=A.val.dtype)
     ok(bh.get_C(colC, valC), "get_C")
     st = bh.stats() if return_stats else None
+    prods = bh.get_row_products() if return_row_products else None
     ok(bh.free_mem(), "free_mem")
     ok(bh.freePlatform(), "freePlatform")
-    return (rowptrC, colC, valC, st) if return_stats else (rowptrC, colC, valC)
+    out = (rowptrC, colC, valC)
+    if return_stats:
+        out += (st,)
+    if return_row_products:
+        out += (prods,)
+    return out

@@ -33,7 +33,7 @@ EXPORTED = [
     "bhb200_create", "bhb200_destroy", "bhb200_set_stream", "bhb200_last_error", "bhb200_device_name",
     "bhb200_sm_count", "bhb200_init_data_f64", "bhb200_init_data_f32", "bhb200_init_data_device",
     "bhb200_warmup", "bhb200_spgemm", "bhb200_synchronize", "bhb200_get_nnzC", "bhb200_get_C_f64",
-    "bhb200_get_C_f32", "bhb200_get_rowptrC_i64", "bhb200_get_C_device", "bhb200_copy_C_to_device", "bhb200_get_row_products",
+    "bhb200_get_C_f32", "bhb200_get_rowptrC_i64", "bhb200_get_C_range", "bhb200_get_C_device", "bhb200_copy_C_to_device", "bhb200_get_row_products",
     "bhb200_get_stats", "bhb200_set_profiling", "bhb200_free_mem", "bhb200_version",
     "bhb200_update_values_f64", "bhb200_update_values_f32", "bhb200_spgemm_numeric",
 ]
@@ -113,6 +113,7 @@ def load(build_if_missing: bool = False):
     L.bhb200_get_C_f64.argtypes = [ctxp, c_void_p, c_void_p, c_void_p]
     L.bhb200_get_C_f32.argtypes = [ctxp, c_void_p, c_void_p, c_void_p]
     L.bhb200_get_rowptrC_i64.argtypes = [ctxp, c_void_p]
+    L.bhb200_get_C_range.argtypes = [ctxp, c_int64, c_int64, c_void_p, c_void_p]
     L.bhb200_get_C_device.argtypes = [ctxp, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     L.bhb200_copy_C_to_device.argtypes = [ctxp, c_void_p, c_void_p, c_void_p]
     L.bhb200_get_row_products.argtypes = [ctxp, c_void_p]

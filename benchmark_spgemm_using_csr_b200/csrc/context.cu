@@ -510,12 +510,14 @@ int bhb200_warmup(bhb200_ctx *ctx)
     int rc = reserve_workspace(ctx);
     if (rc) return rc;
     LaunchCtx lc{ctx->stream, ctx->sm_count, &ctx->launches, ctx->max_span};
-    CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), ctx->stream), "zero counters");
     CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int4>()), "B row ranges kernel");
+    // like the reference's warm-up (bhsparse.h:341-363: compute_nnzCt only) this must leave an existing
+    // result intact: k_row_products rewrites rc[] and the counters, so it is skipped once C exists
+    if (ctx->have_C) return BHB200_SUCCESS;
+    CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), ctx->stream), "zero counters");
     CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int4>(), ctx->prod.as<int>(),
                            ctx->rc.as<int>(), ctx->rlo.as<int>(), ctx->rspan.as<int>(), ctx->counters.as<Counters>()),
        "row products kernel");
-    ctx->have_C = false;
     return BHB200_SUCCESS;
 }
 
@@ -903,6 +905,22 @@ int bhb200_get_C_f64(bhb200_ctx *ctx, int32_t *rowptrC, int32_t *colC, double *v
 int bhb200_get_C_f32(bhb200_ctx *ctx, int32_t *rowptrC, int32_t *colC, float *valC)
 {
     return get_C_any(ctx, BHB200_DTYPE_F32, rowptrC, colC, valC);
+}
+
+int bhb200_get_C_range(bhb200_ctx *ctx, int64_t first, int64_t count, int32_t *colC, void *valC)
+{
+    if (!ctx || !ctx->have_C) return fail(ctx, BHB200_ERR_INVALID, "get_C_range before spgemm");
+    if (first < 0 || count < 0 || first + count > ctx->nnzC) return fail(ctx, BHB200_ERR_INVALID, "range outside [0, nnzC]");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t s = ctx->stream;
+    const size_t vs = vsize(ctx->dtype);
+    if (colC && count > 0)
+        CU(cudaMemcpyAsync(colC, ctx->colC.as<int>() + first, (size_t)count * 4, cudaMemcpyDeviceToHost, s), "D2H colC range");
+    if (valC && count > 0)
+        CU(cudaMemcpyAsync(valC, (const char *)ctx->valC.p + (size_t)first * vs, (size_t)count * vs, cudaMemcpyDeviceToHost, s),
+           "D2H valC range");
+    CU(cudaStreamSynchronize(s), "D2H C range");
+    return BHB200_SUCCESS;
 }
 
 int bhb200_get_rowptrC_i64(bhb200_ctx *ctx, int64_t *rowptrC64)

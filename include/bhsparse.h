@@ -89,6 +89,17 @@ public:
             printf("spgemm error = %d (%s)\n", err, bhb200_last_error(_ctx));
             return err;
         }
+        /* create_C leaves the row pointers of C in the caller's array at the end of spgemm()
+         * (bhsparse_cuda.h:2787-2808); get_C writes them again (:3016).  Results beyond
+         * INT32_MAX entries have no int32 row pointers (get_nnzC() == -1). */
+        if (_rowptrC && bhb200_get_nnzC(_ctx) <= 0x7fffffffLL) {
+#ifdef BHSPARSE_VALUE_FLOAT
+            err = bhb200_get_C_f32(_ctx, _rowptrC, nullptr, nullptr);
+#else
+            err = bhb200_get_C_f64(_ctx, _rowptrC, nullptr, nullptr);
+#endif
+            if (err != BHSPARSE_SUCCESS) return err;
+        }
         if (_verbose) {
             bhb200_stats st;
             bhb200_get_stats(_ctx, &st);

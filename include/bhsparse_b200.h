@@ -117,7 +117,7 @@ BHB200_API int bhb200_init_data_device(bhb200_ctx *ctx, int dtype, int m, int k,
 
 /* -- the hot path --------------------------------------------------------------
  * bhb200_warmup replaces bhsparse::warmup (bhsparse.h:341-363): runs the
- * per-row upper-bound kernel once without touching any result.
+ * per-row upper-bound kernel once; an existing result (C, nnzC) stays valid.
  * bhb200_spgemm replaces bhsparse::spgemm (bhsparse.h:260-339): all four stages
  * on the device.  Unlike the reference it may be called repeatedly.  It returns
  * after the last kernel has been enqueued and the sizes are known; results are
@@ -153,6 +153,10 @@ BHB200_API int64_t bhb200_get_nnzC(const bhb200_ctx *ctx);
 BHB200_API int bhb200_get_C_f64(bhb200_ctx *ctx, int32_t *rowptrC, int32_t *colC, double *valC);
 BHB200_API int bhb200_get_C_f32(bhb200_ctx *ctx, int32_t *rowptrC, int32_t *colC, float *valC);
 BHB200_API int bhb200_get_rowptrC_i64(bhb200_ctx *ctx, int64_t *rowptrC64);
+/* Entries [first, first+count) of colC / valC into HOST arrays (value type of initData; either
+ * pointer may be NULL).  With the int64 row pointers this serves results beyond INT32_MAX
+ * entries piecewise (the reference's int get_C cannot, bhsparse_cuda.h:3011-3020). */
+BHB200_API int bhb200_get_C_range(bhb200_ctx *ctx, int64_t first, int64_t count, int32_t *colC, void *valC);
 /* Device-resident result (borrowed until the next spgemm / free_mem):
  * rowptr32 is NULL-valued when nnz(C) > INT32_MAX. */
 BHB200_API int bhb200_get_C_device(bhb200_ctx *ctx, const int32_t **rowptr32, const int64_t **rowptr64,

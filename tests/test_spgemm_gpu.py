@@ -23,13 +23,15 @@ def _oracle(A, B):
 
 
 def _check(A, B, what, exact=True):
-    got = spgemm(A, B, return_stats=True)
+    got = spgemm(A, B, return_stats=True, return_row_products=True)
     st = got[3]
     want = _oracle(A, B)
     dt = A.val.dtype.type
     assert_csr_equal(got[:3], want, exact_values=exact, rtol=RTOL[dt], what=what)
     prod, total = oracle.row_products(A.rows, A.rowptr, A.col, B.rowptr)
     assert st["products"] == total and st["nnzC"] == want[0][-1]
+    # compute_nnzCt (bhsparse_cuda.h:210-237): the per-row upper bounds, row by row
+    assert np.array_equal(got[4].astype(np.int64), prod), f"{what}: per-row product counts differ"
     return st
 
 
