@@ -88,6 +88,10 @@ class bhsparse:
         self._m = m
         return fn(self._ctx, m, k, n, nnzA, _ptr(valA), _ptr(rpA), _ptr(cA), nnzB, _ptr(valB), _ptr(rpB), _ptr(cB))
 
+    def aliased_operands(self) -> bool:
+        """True if initData got the same host arrays for A and B and uploaded them once."""
+        return bool(self._ctx) and bool(self._lib.bhb200_operands_aliased(self._ctx))
+
     def warmup(self) -> int:
         return self._lib.bhb200_warmup(self._ctx) if self._ctx else capi.ERR_INVALID
 

@@ -31,7 +31,7 @@ NUM_BIN_NAMES = ["c=0", "p=1", "esc<=32", "g64", "g128", "g256", "g512", "g1024"
 # every symbol include/bhsparse_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = [
     "bhb200_create", "bhb200_destroy", "bhb200_set_stream", "bhb200_last_error", "bhb200_device_name",
-    "bhb200_sm_count", "bhb200_init_data_f64", "bhb200_init_data_f32", "bhb200_init_data_device",
+    "bhb200_sm_count", "bhb200_init_data_f64", "bhb200_init_data_f32", "bhb200_init_data_device", "bhb200_operands_aliased",
     "bhb200_warmup", "bhb200_spgemm", "bhb200_synchronize", "bhb200_get_nnzC", "bhb200_get_C_f64",
     "bhb200_get_C_f32", "bhb200_get_rowptrC_i64", "bhb200_get_C_range", "bhb200_get_C_device", "bhb200_copy_C_to_device", "bhb200_get_row_products",
     "bhb200_get_stats", "bhb200_set_profiling", "bhb200_free_mem", "bhb200_version",
@@ -53,6 +53,8 @@ class Stats(ctypes.Structure):
         ("ms_sym_bin", c_float * NUM_BINS), ("ms_num_bin", c_float * NUM_BINS),
         ("direct_rows", c_int64), ("direct_retry_rows", c_int64), ("direct_ct_bytes", c_int64),
         ("direct_bin_mask", c_int64),
+        ("pattern_mode", c_int64), ("pattern_nDA", c_int64), ("pattern_nDB", c_int64), ("pattern_nD", c_int64),
+        ("pattern_acc_len", c_int64), ("spill_bytes", c_int64),
     ]
 
     def as_dict(self) -> dict:
@@ -102,6 +104,7 @@ def load(build_if_missing: bool = False):
     L.bhb200_init_data_f32.argtypes = L.bhb200_init_data_f64.argtypes
     L.bhb200_init_data_device.argtypes = [ctxp, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                           c_int, c_void_p, c_void_p, c_void_p]
+    L.bhb200_operands_aliased.argtypes = [ctxp]
     L.bhb200_warmup.argtypes = [ctxp]
     L.bhb200_spgemm.argtypes = [ctxp]
     L.bhb200_synchronize.argtypes = [ctxp]

@@ -122,6 +122,8 @@ struct Counters {
     unsigned long long pool_cursor;  // word-list pool: entries handed out by the symbolic range kernel
     int max_row_products;
     int row_overflow;              // a row's product count did not fit int32
+    int bad_B;                     // a row of B is not strictly ascending / has a column outside [0, n)
+    int bad_A;                     // a column of A is outside [0, k)
     int sym_bin[MAX_BINS];
     int num_bin[MAX_BINS];
     int sym_cursor[MAX_BINS];
@@ -531,8 +533,8 @@ struct LaunchCtx {
 };
 
 // stage_count.cu
-cudaError_t launch_b_row_ranges(const LaunchCtx &lc, int k, Csr B, int4 *brange);
-cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, const int4 *brange, int *prod,
+cudaError_t launch_b_row_ranges(const LaunchCtx &lc, int k, int n, Csr B, int4 *brange, Counters *ctr);
+cudaError_t launch_row_products(const LaunchCtx &lc, int m, int k, int nnzA, Csr A, Csr B, const int4 *brange, int *prod,
                                 int *rc, int *rlo, int *rspan, Counters *ctr);
 // spec_mask: bit b set = symbolic bin b ran in direct mode (rows with ct_off >= 0 go to NB_COPY)
 cudaError_t launch_bin_scatter(const LaunchCtx &lc, bool numeric, int m, const int *prod, const int *rc,

@@ -6,6 +6,7 @@
 // O(m) data plus 3 per merge round.
 #include "../../include/bhsparse_b200.h"
 #include "common.cuh"
+#include "pattern_plan.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -20,15 +21,22 @@ namespace {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool host = false;   // spilled: pinned, device-mapped HOST memory (see reserve_spillable)
+    void drop(size_t *total)
+    {
+        if (p) {
+            if (host) cudaFreeHost(p);
+            else cudaFree(p);
+            *total -= cap;
+        }
+        p = nullptr;
+        cap = 0;
+        host = false;
+    }
     cudaError_t reserve(size_t bytes, size_t *total)
     {
         if (bytes <= cap) return cudaSuccess;
-        if (p) {
-            cudaFree(p);
-            *total -= cap;
-            p = nullptr;
-            cap = 0;
-        }
+        drop(total);
         // round up to 256 B; grow-only cache, released by free_mem
         size_t want = (bytes + 255) & ~(size_t)255;
         cudaError_t e = cudaMalloc(&p, want);
@@ -40,15 +48,32 @@ struct DevBuf {
         *total += cap;
         return cudaSuccess;
     }
-    void release(size_t *total)
+    // Host-memory spill (the reference's OpenCL build keeps Ct in host-coherent
+    // "re-allocatable" memory for the same reason, SpGEMM_opencl/bhsparse_opencl.cpp:219-227,
+    // 441-454, 832-863): if the device cannot hold the buffer -- cudaMalloc fails, or the request
+    // exceeds `device_cap` (BHB200_DEBUG_DEVICE_CAP, tests) -- it is placed in pinned host memory
+    // mapped into the device address space; kernels then write it across NVLink-C2C / PCIe.
+    cudaError_t reserve_spillable(size_t bytes, size_t *total, size_t device_cap, bool *spilled)
     {
-        if (p) {
-            cudaFree(p);
-            *total -= cap;
+        if (bytes <= cap) return cudaSuccess;
+        cudaError_t e = cudaErrorMemoryAllocation;
+        if (bytes <= device_cap) e = reserve(bytes, total);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();
+        drop(total);
+        size_t want = (bytes + 4095) & ~(size_t)4095;
+        e = cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
         }
-        p = nullptr;
-        cap = 0;
+        cap = want;
+        host = true;
+        *total += cap;
+        if (spilled) *spilled = true;
+        return cudaSuccess;
     }
+    void release(size_t *total) { drop(total); }
     template <typename T>
     T *as() const
     {
@@ -69,6 +94,7 @@ struct bhb200_ctx {
     // operands
     bool have_data = false;
     bool borrowed = false;
+    bool aliased = false;   // host API: A and B were the same host arrays, uploaded once
     int dtype = BHB200_DTYPE_F64;
     int m = 0, k = 0, n = 0, nnzA = 0, nnzB = 0;
     DevBuf a_rowptr, a_col, a_val, b_rowptr, b_col, b_val;
@@ -78,6 +104,15 @@ struct bhb200_ctx {
     DevBuf prod, rc, queue, rowoff64, rowptr32, blocksums, counters, bitmap, prefix;
     DevBuf brange, rlo, rspan, wl_off, wl_cnt, wl_idx, wl_bits;   // span info + word-list pool (range kernels)
     DevBuf ct_off, ct_col, ct_val, retry_q;                       // direct mode: staging buffer (Ct) + retry queues
+    // diagonal-pattern mode (stage_pattern.cuh): offset sets, per-entry codes, masks, tables
+    DevBuf pat_sets, pat_ta, pat_tb, pat_maskB, pat_outmask, pat_tables;
+    PatSet *h_sets = nullptr;    // pinned, [2]
+    PatternPlan plan;
+    size_t device_cap = ~(size_t)0;   // BHB200_DEBUG_DEVICE_CAP: largest single buffer the device may hold (tests)
+    int pattern_enable = 1;      // BHB200_PATTERN=off disables
+    bool last_pattern = false;   // the last product ran in pattern mode
+    PatTables last_tables{};
+    const unsigned char *last_ta = nullptr, *last_tb = nullptr;
     int direct_mode = 1;                                          // BHB200_DIRECT=off disables
     int direct_wide = 1;                                          // BHB200_DIRECT=tight: speculated capacities <= 128 only
     size_t bitmap_zeroed_bytes = 0;
@@ -145,7 +180,9 @@ void release_operands(bhb200_ctx *ctx)
     ctx->B = Csr{nullptr, nullptr, nullptr};
     ctx->have_data = false;
     ctx->borrowed = false;
+    ctx->aliased = false;
     ctx->have_C = false;
+    ctx->last_pattern = false;
     ctx->nnzC = 0;
 }
 
@@ -173,23 +210,29 @@ int init_host(bhb200_ctx *ctx, int dtype, int m, int k, int n, int nnzA, const v
     CU(ctx->a_rowptr.reserve((size_t)(m + 1) * 4, &ctx->dev_bytes), "alloc rowptrA");
     CU(ctx->a_col.reserve((size_t)nnzA * 4 + 4, &ctx->dev_bytes), "alloc colA");
     CU(ctx->a_val.reserve((size_t)nnzA * vs + 8, &ctx->dev_bytes), "alloc valA");
-    CU(ctx->b_rowptr.reserve((size_t)(k + 1) * 4, &ctx->dev_bytes), "alloc rowptrB");
-    CU(ctx->b_col.reserve((size_t)nnzB * 4 + 4, &ctx->dev_bytes), "alloc colB");
-    CU(ctx->b_val.reserve((size_t)nnzB * vs + 8, &ctx->dev_bytes), "alloc valB");
+    // C = A*A with the SAME host arrays passed twice (the reference driver's stock workloads build
+    // A and B identically, main.cu:32-51): one upload, both operands point at it
+    const bool alias = m == k && nnzA == nnzB && rowptrA == rowptrB && colA == colB && valA == valB;
+    if (!alias) {
+        CU(ctx->b_rowptr.reserve((size_t)(k + 1) * 4, &ctx->dev_bytes), "alloc rowptrB");
+        CU(ctx->b_col.reserve((size_t)nnzB * 4 + 4, &ctx->dev_bytes), "alloc colB");
+        CU(ctx->b_val.reserve((size_t)nnzB * vs + 8, &ctx->dev_bytes), "alloc valB");
+    }
     cudaStream_t s = ctx->stream;
     CU(cudaMemcpyAsync(ctx->a_rowptr.p, rowptrA, (size_t)(m + 1) * 4, cudaMemcpyHostToDevice, s), "H2D rowptrA");
-    CU(cudaMemcpyAsync(ctx->b_rowptr.p, rowptrB, (size_t)(k + 1) * 4, cudaMemcpyHostToDevice, s), "H2D rowptrB");
+    if (!alias) CU(cudaMemcpyAsync(ctx->b_rowptr.p, rowptrB, (size_t)(k + 1) * 4, cudaMemcpyHostToDevice, s), "H2D rowptrB");
     if (nnzA > 0) {
         CU(cudaMemcpyAsync(ctx->a_col.p, colA, (size_t)nnzA * 4, cudaMemcpyHostToDevice, s), "H2D colA");
         CU(cudaMemcpyAsync(ctx->a_val.p, valA, (size_t)nnzA * vs, cudaMemcpyHostToDevice, s), "H2D valA");
     }
-    if (nnzB > 0) {
+    if (nnzB > 0 && !alias) {
         CU(cudaMemcpyAsync(ctx->b_col.p, colB, (size_t)nnzB * 4, cudaMemcpyHostToDevice, s), "H2D colB");
         CU(cudaMemcpyAsync(ctx->b_val.p, valB, (size_t)nnzB * vs, cudaMemcpyHostToDevice, s), "H2D valB");
     }
     CU(cudaStreamSynchronize(s), "H2D operands");
     ctx->A = Csr{ctx->a_rowptr.as<int>(), ctx->a_col.as<int>(), ctx->a_val.p};
-    ctx->B = Csr{ctx->b_rowptr.as<int>(), ctx->b_col.as<int>(), ctx->b_val.p};
+    ctx->B = alias ? ctx->A : Csr{ctx->b_rowptr.as<int>(), ctx->b_col.as<int>(), ctx->b_val.p};
+    ctx->aliased = alias;
     ctx->dtype = dtype;
     ctx->m = m;
     ctx->k = k;
@@ -347,6 +390,102 @@ int run_numeric_bins(bhb200_ctx *ctx, const LaunchCtx &lc, const int *num_bin, c
 }
 
 
+void finish_stats(bhb200_ctx *ctx)
+{
+    bhb200_stats &st = ctx->stats;
+    st.kernel_launches = ctx->launches;
+    const int64_t v = (int64_t)vsize(ctx->dtype);
+    const int64_t m1 = (int64_t)ctx->m + 1;
+    st.bytes_algorithmic = (m1 * 4 + (int64_t)ctx->nnzA * (4 + v)) + ((int64_t)ctx->nnzA * 8 + st.products * (4 + v)) +
+                           (m1 * 4 + ctx->nnzC * (4 + v));
+    st.bytes_compulsory = (m1 * 4 + (int64_t)ctx->nnzA * (4 + v)) + (((int64_t)ctx->k + 1) * 4 + (int64_t)ctx->nnzB * (4 + v)) +
+                          (m1 * 4 + ctx->nnzC * (4 + v));
+    st.workspace_bytes = (int64_t)ctx->dev_bytes;
+}
+
+// Diagonal-pattern mode (stage_pattern.cuh).  Called after the stage-1 sync with the offset sets of
+// A and B in ctx->h_sets.  Returns PATTERN_NOT_APPLICABLE if the operands do not qualify (the
+// caller continues with the general path), otherwise the result of the whole product.
+constexpr int PATTERN_NOT_APPLICABLE = 1;
+
+int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab)
+{
+    const PatSet &sb = ctx->h_sets[1];
+    const PatSet &sa = same_ab ? ctx->h_sets[1] : ctx->h_sets[0];
+    if (sa.overflow || sb.overflow || sa.count > PAT_MAX_OFFS || sb.count > PAT_MAX_OFFS) return PATTERN_NOT_APPLICABLE;
+    const int FILL = PAT_EMPTY;   // what the memset left in unused slots
+    int offA[PAT_MAX_OFFS], offB[PAT_MAX_OFFS], nA = 0, nB = 0;
+    for (int i = 0; i < PAT_SET_SLOTS; ++i) {
+        if (sa.slot[i] != FILL && nA < PAT_MAX_OFFS) offA[nA++] = sa.slot[i];
+        if (sb.slot[i] != FILL && nB < PAT_MAX_OFFS) offB[nB++] = sb.slot[i];
+    }
+    if (nA != sa.count || nB != sb.count) return PATTERN_NOT_APPLICABLE;
+    const size_t vs = vsize(ctx->dtype);
+    if (!build_pattern_plan(offA, nA, offB, nB, (int)vs, ctx->plan)) return PATTERN_NOT_APPLICABLE;
+    const PatternPlan &plan = ctx->plan;
+    cudaStream_t s = ctx->stream;
+    bhb200_stats &st = ctx->stats;
+    // workspace; any allocation failure falls back to the general path
+    const size_t need_tab = plan.blob.size();
+    const bool had_tables = ctx->pat_tables.cap >= need_tab && plan.reused;
+    if (ctx->pat_tables.reserve(need_tab, &ctx->dev_bytes) != cudaSuccess ||
+        ctx->pat_tb.reserve((size_t)ctx->nnzB + 16, &ctx->dev_bytes) != cudaSuccess ||
+        (!same_ab && ctx->pat_ta.reserve((size_t)ctx->nnzA + 16, &ctx->dev_bytes) != cudaSuccess) ||
+        ctx->pat_maskB.reserve(((size_t)ctx->k + 1) * 8, &ctx->dev_bytes) != cudaSuccess ||
+        ctx->pat_outmask.reserve(((size_t)ctx->m + 1) * plan.nw * 4, &ctx->dev_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->plan = PatternPlan();
+        return PATTERN_NOT_APPLICABLE;
+    }
+    if (!had_tables)
+        CU(cudaMemcpyAsync(ctx->pat_tables.p, plan.blob.data(), need_tab, cudaMemcpyHostToDevice, s), "H2D pattern tables");
+    const PatTables t = pattern_tables(plan, ctx->pat_tables.as<unsigned char>());
+    unsigned char *tb = ctx->pat_tb.as<unsigned char>();
+    unsigned char *ta = same_ab ? tb : ctx->pat_ta.as<unsigned char>();
+    CU(launch_pat_codes(lc, ctx->k, ctx->B.rowptr, ctx->B.col, t.offsB, t.nDB, tb, ctx->pat_maskB.as<unsigned long long>()),
+       "pattern codes of B");
+    if (!same_ab) CU(launch_pat_codes(lc, ctx->m, ctx->A.rowptr, ctx->A.col, t.offsA, t.nDA, ta, nullptr), "pattern codes of A");
+    CU(cudaEventRecord(ctx->ev[1], s), "event");
+    int *rcnt = ctx->rc.as<int>();
+    Counters *d_ctr = ctx->counters.as<Counters>();
+    CU(launch_pat_symbolic(lc, ctx->m, ctx->A, ta, ctx->pat_maskB.as<unsigned long long>(), t, ctx->pat_outmask.as<unsigned>(), rcnt),
+       "pattern symbolic");
+    CU(cudaEventRecord(ctx->ev[2], s), "event");
+    memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
+    CU(launch_scan(lc, ctx->m, ctx->A.rowptr, ctx->prod.as<int>(), rcnt, ctx->rspan.as<int>(), 0u, nullptr,
+                   ctx->rowoff64.as<int64_t>(), ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
+       "row pointer scan");
+    CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
+    CU(cudaStreamSynchronize(s), "pattern symbolic / scan");
+    ctx->nnzC = (int64_t)ctx->h_ctr->nnzC;
+    st.nnzC = ctx->nnzC;
+    {
+        bool spilled = false;
+        CU(ctx->colC.reserve_spillable((size_t)ctx->nnzC * 4 + 16, &ctx->dev_bytes, ctx->device_cap, &spilled), "alloc colC");
+        CU(ctx->valC.reserve_spillable((size_t)ctx->nnzC * vs + 16, &ctx->dev_bytes, ctx->device_cap, &spilled), "alloc valC");
+        st.spill_bytes += (ctx->colC.host ? (int64_t)ctx->colC.cap : 0) + (ctx->valC.host ? (int64_t)ctx->valC.cap : 0);
+    }
+    CU(cudaEventRecord(ctx->ev[3], s), "event");
+    CU(launch_pat_numeric(lc, ctx->dtype, ctx->m, ctx->A, ctx->B, ta, tb, t, ctx->pat_outmask.as<unsigned>(),
+                          ctx->rowoff64.as<int64_t>(), ctx->colC.as<int>(), ctx->valC.p),
+       "pattern numeric");
+    CU(cudaEventRecord(ctx->ev[4], s), "event");
+    st.pattern_mode = 1;
+    st.pattern_nDA = t.nDA;
+    st.pattern_nDB = t.nDB;
+    st.pattern_nD = t.nD;
+    st.pattern_acc_len = t.acc_len;
+    finish_stats(ctx);
+    ctx->last_pattern = true;
+    ctx->last_tables = t;
+    ctx->last_ta = ta;
+    ctx->last_tb = tb;
+    ctx->have_C = true;
+    ctx->timing_valid = true;
+    return BHB200_SUCCESS;
+}
+
+
 }  // namespace
 
 // ============================================================================
@@ -392,6 +531,13 @@ int bhb200_create(bhb200_ctx **out, int device)
         return BHB200_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (cudaHostAlloc((void **)&ctx->h_sets, 2 * sizeof(PatSet), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return BHB200_ERR_CUDA;
+    }
+    if (const char *pm = getenv("BHB200_PATTERN")) ctx->pattern_enable = strcmp(pm, "off") != 0;
+    if (const char *dc = getenv("BHB200_DEBUG_DEVICE_CAP")) ctx->device_cap = (size_t)atoll(dc);
     if (const char *dm = getenv("BHB200_DIRECT")) {
         ctx->direct_mode = strcmp(dm, "off") != 0;
         ctx->direct_wide = strcmp(dm, "tight") != 0;
@@ -418,7 +564,10 @@ int bhb200_free_mem(bhb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     release_operands(ctx);
-    DevBuf *bufs[] = {&ctx->ct_off, &ctx->ct_col, &ctx->ct_val, &ctx->retry_q,
+    ctx->plan = PatternPlan();
+    ctx->last_pattern = false;
+    DevBuf *bufs[] = {&ctx->pat_sets, &ctx->pat_ta, &ctx->pat_tb, &ctx->pat_maskB, &ctx->pat_outmask, &ctx->pat_tables,
+                      &ctx->ct_off, &ctx->ct_col, &ctx->ct_val, &ctx->retry_q,
                       &ctx->brange, &ctx->rlo, &ctx->rspan, &ctx->wl_off, &ctx->wl_cnt, &ctx->wl_idx, &ctx->wl_bits,
                       &ctx->prod, &ctx->rc, &ctx->queue, &ctx->rowoff64, &ctx->rowptr32, &ctx->blocksums,
                       &ctx->counters, &ctx->bitmap, &ctx->prefix, &ctx->colC, &ctx->valC};
@@ -439,6 +588,7 @@ int bhb200_destroy(bhb200_ctx *ctx)
             if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->h_sets) cudaFreeHost(ctx->h_sets);
     cudaGetLastError();
     delete ctx;
     return BHB200_SUCCESS;
@@ -510,12 +660,12 @@ int bhb200_warmup(bhb200_ctx *ctx)
     int rc = reserve_workspace(ctx);
     if (rc) return rc;
     LaunchCtx lc{ctx->stream, ctx->sm_count, &ctx->launches, ctx->max_span};
-    CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int4>()), "B row ranges kernel");
+    CU(launch_b_row_ranges(lc, ctx->k, ctx->n, ctx->B, ctx->brange.as<int4>(), ctx->counters.as<Counters>()), "B row ranges kernel");
     // like the reference's warm-up (bhsparse.h:341-363: compute_nnzCt only) this must leave an existing
     // result intact: k_row_products rewrites rc[] and the counters, so it is skipped once C exists
     if (ctx->have_C) return BHB200_SUCCESS;
     CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), ctx->stream), "zero counters");
-    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int4>(), ctx->prod.as<int>(),
+    CU(launch_row_products(lc, ctx->m, ctx->k, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int4>(), ctx->prod.as<int>(),
                            ctx->rc.as<int>(), ctx->rlo.as<int>(), ctx->rspan.as<int>(), ctx->counters.as<Counters>()),
        "row products kernel");
     return BHB200_SUCCESS;
@@ -551,18 +701,42 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     // ---- stage 1: upper bound per row + symbolic bins ----
     CU(cudaEventRecord(ctx->ev[0], s), "event");
     CU(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s), "zero counters");
+    // diagonal-pattern mode: exact offset sets of A and B, read back with the stage-1 counters
+    ctx->last_pattern = false;
+    const bool same_ab = ctx->A.rowptr == ctx->B.rowptr && ctx->A.col == ctx->B.col && ctx->m == ctx->k;
+    bool try_pattern = ctx->pattern_enable && ctx->m > 0 && ctx->nnzA > 0 && ctx->nnzB > 0;
+    if (try_pattern && ctx->pat_sets.reserve(2 * sizeof(PatSet), &ctx->dev_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        try_pattern = false;
+    }
+    if (try_pattern) {
+        PatSet *sets = ctx->pat_sets.as<PatSet>();
+        CU(cudaMemsetAsync(sets, 0x80, 2 * sizeof(PatSet), s), "init offset sets");   // slots = PAT_EMPTY-like filler
+        CU(cudaMemsetAsync(&sets[0], 0, 8, s), "init offset sets");
+        CU(cudaMemsetAsync(&sets[1], 0, 8, s), "init offset sets");
+        CU(launch_offset_set(lc, ctx->k, ctx->B.rowptr, ctx->B.col, &sets[1]), "offset set of B");
+        if (!same_ab) CU(launch_offset_set(lc, ctx->m, ctx->A.rowptr, ctx->A.col, &sets[0]), "offset set of A");
+    }
     int *rlo = ctx->rlo.as<int>();
     int *rspan = ctx->rspan.as<int>();
-    CU(launch_b_row_ranges(lc, ctx->k, ctx->B, ctx->brange.as<int4>()), "B row ranges kernel");
-    CU(launch_row_products(lc, ctx->m, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int4>(), prod, rcnt, rlo, rspan, d_ctr),
+    CU(launch_b_row_ranges(lc, ctx->k, ctx->n, ctx->B, ctx->brange.as<int4>(), ctx->counters.as<Counters>()), "B row ranges kernel");
+    CU(launch_row_products(lc, ctx->m, ctx->k, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int4>(), prod, rcnt, rlo, rspan, d_ctr),
        "row products kernel");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
+    if (try_pattern)
+        CU(cudaMemcpyAsync(ctx->h_sets, ctx->pat_sets.p, 2 * sizeof(PatSet), cudaMemcpyDeviceToHost, s), "D2H offset sets");
     CU(cudaStreamSynchronize(s), "stage 1");
     Counters hc = *ctx->h_ctr;
+    if (hc.bad_B) return fail(ctx, BHB200_ERR_INVALID, "rows of B must be sorted by column, duplicate-free and inside [0, n)");
+    if (hc.bad_A) return fail(ctx, BHB200_ERR_INVALID, "a column index of A is outside [0, k)");
     if (hc.row_overflow) return fail(ctx, BHB200_ERR_OVERFLOW, "a row has more than INT32_MAX intermediate products");
     st.products = (int64_t)hc.products;
     st.max_row_products = hc.max_row_products;
     for (int b = 0; b < BHB200_NUM_SYM_BINS && b < MAX_BINS; ++b) st.sym_bin_rows[b] = hc.sym_bin[b];
+    if (try_pattern) {
+        rc = run_pattern(ctx, lc, same_ab);
+        if (rc != PATTERN_NOT_APPLICABLE) return rc;
+    }
     // lanes per row group: follow the average length of the B rows actually referenced
     const double avg_b = ctx->nnzA > 0 ? (double)hc.products / (double)ctx->nnzA : 0.0;
     const int G = avg_b <= 10.0 ? 8 : 32;
@@ -654,13 +828,17 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         }
         if (spec_mask) {
             const size_t m1 = (size_t)ctx->m + 1;
+            // the staging buffer (the reference's Ct) may spill to host memory like C itself
+            bool spilled = false;
             if (ctx->ct_off.reserve(m1 * 8, &ctx->dev_bytes) != cudaSuccess ||
                 ctx->retry_q.reserve(m1 * 4, &ctx->dev_bytes) != cudaSuccess ||
-                ctx->ct_col.reserve((size_t)ct_entries * 4 + 16, &ctx->dev_bytes) != cudaSuccess ||
-                ctx->ct_val.reserve((size_t)ct_entries * vs + 16, &ctx->dev_bytes) != cudaSuccess) {
+                ctx->ct_col.reserve_spillable((size_t)ct_entries * 4 + 16, &ctx->dev_bytes, ctx->device_cap, &spilled) != cudaSuccess ||
+                ctx->ct_val.reserve_spillable((size_t)ct_entries * vs + 16, &ctx->dev_bytes, ctx->device_cap, &spilled) != cudaSuccess) {
                 cudaGetLastError();
                 spec_mask = 0;   // no room for the staging buffer: two-pass path for everything
             }
+            if (spec_mask)
+                st.spill_bytes += (ctx->ct_col.host ? (int64_t)ctx->ct_col.cap : 0) + (ctx->ct_val.host ? (int64_t)ctx->ct_val.cap : 0);
         }
     }
     st.direct_rows = 0;
@@ -747,8 +925,12 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         st.num_bin_nnzC[b] = (int64_t)hc.num_bin_nnzc[b];
         st.num_bin_nnzA[b] = (int64_t)hc.num_bin_nnza[b];
     }
-    CU(ctx->colC.reserve((size_t)ctx->nnzC * 4 + 16, &ctx->dev_bytes), "alloc colC");
-    CU(ctx->valC.reserve((size_t)ctx->nnzC * vs + 16, &ctx->dev_bytes), "alloc valC");
+    {
+        bool spilled = false;
+        CU(ctx->colC.reserve_spillable((size_t)ctx->nnzC * 4 + 16, &ctx->dev_bytes, ctx->device_cap, &spilled), "alloc colC");
+        CU(ctx->valC.reserve_spillable((size_t)ctx->nnzC * vs + 16, &ctx->dev_bytes, ctx->device_cap, &spilled), "alloc valC");
+        st.spill_bytes += (ctx->colC.host ? (int64_t)ctx->colC.cap : 0) + (ctx->valC.host ? (int64_t)ctx->valC.cap : 0);
+    }
     BinOffsets no;
     offsets_from_counts(hc.num_bin, no);
     CU(launch_bin_scatter(lc, true, ctx->m, prod, rcnt, rspan, spec_mask, ctx->ct_off.as<long long>(), no, d_ctr, queue),
@@ -770,14 +952,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(stamp(ctx, 1, MAX_BINS), "event");
     CU(cudaEventRecord(ctx->ev[4], s), "event");
 
-    st.kernel_launches = ctx->launches;
-    const int64_t v = (int64_t)vs;
-    const int64_t m1 = (int64_t)ctx->m + 1;
-    st.bytes_algorithmic = (m1 * 4 + (int64_t)ctx->nnzA * (4 + v)) + ((int64_t)ctx->nnzA * 8 + st.products * (4 + v)) +
-                           (m1 * 4 + ctx->nnzC * (4 + v));
-    st.bytes_compulsory = (m1 * 4 + (int64_t)ctx->nnzA * (4 + v)) + (((int64_t)ctx->k + 1) * 4 + (int64_t)ctx->nnzB * (4 + v)) +
-                          (m1 * 4 + ctx->nnzC * (4 + v));
-    st.workspace_bytes = (int64_t)ctx->dev_bytes;
+    finish_stats(ctx);
     ctx->last_G = G;
     ctx->last_wl = wl;
     ctx->have_C = true;
@@ -804,6 +979,17 @@ int bhb200_spgemm_numeric(bhb200_ctx *ctx)
     CU(cudaEventRecord(ctx->ev[1], s), "event");
     CU(cudaEventRecord(ctx->ev[2], s), "event");
     memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
+    if (ctx->last_pattern) {
+        // pattern mode: codes, masks, tables and row pointers are still valid -- one kernel
+        CU(cudaEventRecord(ctx->ev[3], s), "event");
+        CU(launch_pat_numeric(lc, ctx->dtype, ctx->m, ctx->A, ctx->B, ctx->last_ta, ctx->last_tb, ctx->last_tables,
+                              ctx->pat_outmask.as<unsigned>(), ctx->rowoff64.as<int64_t>(), ctx->colC.as<int>(), ctx->valC.p),
+           "pattern numeric");
+        CU(cudaEventRecord(ctx->ev[4], s), "event");
+        st.kernel_launches = ctx->launches;
+        ctx->timing_valid = true;
+        return BHB200_SUCCESS;
+    }
     if (!ctx->reuse_bins_valid) {
         // numeric bins of ALL rows (the direct-mode rows of the full product sit in the copy bin)
         CU(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s), "zero counters");
@@ -843,9 +1029,23 @@ static int update_values_any(bhb200_ctx *ctx, int dtype, const void *valA, const
     if (dtype != ctx->dtype) return fail(ctx, BHB200_ERR_INVALID, "value type differs from initData");
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     const size_t vs = vsize(ctx->dtype);
+    if (ctx->aliased && (valA || valB) && valA != valB) {
+        // A and B share one device copy (same host arrays in initData) but now get different values:
+        // give B its own copy (patterns unchanged, so every cached structure stays valid)
+        CU(ctx->b_rowptr.reserve((size_t)(ctx->k + 1) * 4, &ctx->dev_bytes), "alloc rowptrB");
+        CU(ctx->b_col.reserve((size_t)ctx->nnzB * 4 + 4, &ctx->dev_bytes), "alloc colB");
+        CU(ctx->b_val.reserve((size_t)ctx->nnzB * vs + 8, &ctx->dev_bytes), "alloc valB");
+        CU(cudaMemcpyAsync(ctx->b_rowptr.p, ctx->a_rowptr.p, (size_t)(ctx->k + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream), "D2D rowptrB");
+        if (ctx->nnzB > 0) {
+            CU(cudaMemcpyAsync(ctx->b_col.p, ctx->a_col.p, (size_t)ctx->nnzB * 4, cudaMemcpyDeviceToDevice, ctx->stream), "D2D colB");
+            CU(cudaMemcpyAsync(ctx->b_val.p, ctx->a_val.p, (size_t)ctx->nnzB * vs, cudaMemcpyDeviceToDevice, ctx->stream), "D2D valB");
+        }
+        ctx->B = Csr{ctx->b_rowptr.as<int>(), ctx->b_col.as<int>(), ctx->b_val.p};
+        ctx->aliased = false;
+    }
     if (valA && ctx->nnzA > 0)
         CU(cudaMemcpyAsync(ctx->a_val.p, valA, (size_t)ctx->nnzA * vs, cudaMemcpyHostToDevice, ctx->stream), "H2D valA");
-    if (valB && ctx->nnzB > 0)
+    if (valB && ctx->nnzB > 0 && !ctx->aliased)   // (still aliased: valB == valA, the shared copy has just been written)
         CU(cudaMemcpyAsync(ctx->b_val.p, valB, (size_t)ctx->nnzB * vs, cudaMemcpyHostToDevice, ctx->stream), "H2D valB");
     CU(cudaStreamSynchronize(ctx->stream), "update values");
     return BHB200_SUCCESS;
@@ -876,6 +1076,11 @@ int bhb200_synchronize(bhb200_ctx *ctx)
     return BHB200_SUCCESS;
 }
 
+int bhb200_operands_aliased(const bhb200_ctx *ctx)
+{
+    return (ctx && ctx->have_data && ctx->aliased) ? 1 : 0;
+}
+
 int64_t bhb200_get_nnzC(const bhb200_ctx *ctx)
 {
     return (ctx && ctx->have_C) ? ctx->nnzC : -1;
@@ -891,9 +1096,9 @@ static int get_C_any(bhb200_ctx *ctx, int dtype, int32_t *rowptrC, int32_t *colC
     if (rowptrC)
         CU(cudaMemcpyAsync(rowptrC, ctx->rowptr32.p, ((size_t)ctx->m + 1) * 4, cudaMemcpyDeviceToHost, s), "D2H rowptrC");
     if (colC && ctx->nnzC > 0)
-        CU(cudaMemcpyAsync(colC, ctx->colC.p, (size_t)ctx->nnzC * 4, cudaMemcpyDeviceToHost, s), "D2H colC");
+        CU(cudaMemcpyAsync(colC, ctx->colC.p, (size_t)ctx->nnzC * 4, cudaMemcpyDefault, s), "D2H colC");
     if (valC && ctx->nnzC > 0)
-        CU(cudaMemcpyAsync(valC, ctx->valC.p, (size_t)ctx->nnzC * vsize(dtype), cudaMemcpyDeviceToHost, s), "D2H valC");
+        CU(cudaMemcpyAsync(valC, ctx->valC.p, (size_t)ctx->nnzC * vsize(dtype), cudaMemcpyDefault, s), "D2H valC");
     CU(cudaStreamSynchronize(s), "D2H C");
     return BHB200_SUCCESS;
 }
@@ -915,9 +1120,9 @@ int bhb200_get_C_range(bhb200_ctx *ctx, int64_t first, int64_t count, int32_t *c
     cudaStream_t s = ctx->stream;
     const size_t vs = vsize(ctx->dtype);
     if (colC && count > 0)
-        CU(cudaMemcpyAsync(colC, ctx->colC.as<int>() + first, (size_t)count * 4, cudaMemcpyDeviceToHost, s), "D2H colC range");
+        CU(cudaMemcpyAsync(colC, ctx->colC.as<int>() + first, (size_t)count * 4, cudaMemcpyDefault, s), "D2H colC range");
     if (valC && count > 0)
-        CU(cudaMemcpyAsync(valC, (const char *)ctx->valC.p + (size_t)first * vs, (size_t)count * vs, cudaMemcpyDeviceToHost, s),
+        CU(cudaMemcpyAsync(valC, (const char *)ctx->valC.p + (size_t)first * vs, (size_t)count * vs, cudaMemcpyDefault, s),
            "D2H valC range");
     CU(cudaStreamSynchronize(s), "D2H C range");
     return BHB200_SUCCESS;
@@ -952,9 +1157,9 @@ int bhb200_copy_C_to_device(bhb200_ctx *ctx, int64_t *rowptrC64, int32_t *colC, 
     if (rowptrC64)
         CU(cudaMemcpyAsync(rowptrC64, ctx->rowoff64.p, ((size_t)ctx->m + 1) * 8, cudaMemcpyDeviceToDevice, s), "D2D rowptrC64");
     if (colC && ctx->nnzC > 0)
-        CU(cudaMemcpyAsync(colC, ctx->colC.p, (size_t)ctx->nnzC * 4, cudaMemcpyDeviceToDevice, s), "D2D colC");
+        CU(cudaMemcpyAsync(colC, ctx->colC.p, (size_t)ctx->nnzC * 4, cudaMemcpyDefault, s), "D2D colC");
     if (valC && ctx->nnzC > 0)
-        CU(cudaMemcpyAsync(valC, ctx->valC.p, (size_t)ctx->nnzC * vsize(ctx->dtype), cudaMemcpyDeviceToDevice, s), "D2D valC");
+        CU(cudaMemcpyAsync(valC, ctx->valC.p, (size_t)ctx->nnzC * vsize(ctx->dtype), cudaMemcpyDefault, s), "D2D valC");
     CU(cudaStreamSynchronize(s), "D2D C");
     return BHB200_SUCCESS;
 }

@@ -17,20 +17,44 @@ namespace bhb {
 // ({.., 0, INT_MAX, -1} for empty rows).  k_row_products then needs ONE aligned 16-byte gather per
 // entry of A for both the product count and the column span of the row of C (instead of
 // rowptrB[k], rowptrB[k+1] and two columns).
-__global__ void __launch_bounds__(256) k_b_row_ranges(const int k, const int *__restrict__ rowptrB,
-                                                      const int *__restrict__ colB, int4 *__restrict__ brange)
+// The kernel reads EVERY column of B (8 lanes per row): min / max are taken over the whole row and
+// the precondition of the whole pipeline -- columns of a B row strictly ascending (sorted, no
+// duplicates; the reference's merge kernels need the same, bhsparse_cuda.h:1730,1762) and inside
+// [0, n) -- is checked on the way.  A violation raises ctr->bad_B and bhb200_spgemm returns
+// BHB200_ERR_INVALID instead of corrupting shared memory (range kernels) or losing duplicate
+// contributions (the hash kernels' non-atomic accumulate).
+__global__ void __launch_bounds__(256) k_b_row_ranges(const int k, const int n, const int *__restrict__ rowptrB,
+                                                      const int *__restrict__ colB, int4 *__restrict__ brange,
+                                                      Counters *__restrict__ ctr)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= k) return;
+    const int gl = threadIdx.x & 7;
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (r >= k) return;   // (whole 8-lane groups leave together)
+    const unsigned gmask = group_mask<8>(threadIdx.x & 31);
     const int s = rowptrB[r], e = rowptrB[r + 1];
-    brange[r] = (e > s) ? make_int4(s, e - s, colB[s], colB[e - 1]) : make_int4(s, 0, 0x7fffffff, -1);
+    int lo = 0x7fffffff, hi = -1;
+    bool bad = false;
+    for (int p = s + gl; p < e; p += 8) {
+        const int c = colB[p];
+        lo = min(lo, c);
+        hi = max(hi, c);
+        bad |= (p > s && colB[p - 1] >= c);
+    }
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(gmask, lo, d, 8));
+        hi = max(hi, __shfl_xor_sync(gmask, hi, d, 8));
+    }
+    bad |= e < s || (e > s && (lo < 0 || hi >= n));
+    if (bad) ctr->bad_B = 1;
+    if (gl == 0) brange[r] = (e > s) ? make_int4(s, e - s, lo, hi) : make_int4(s, 0, 0x7fffffff, -1);
 }
 
-cudaError_t launch_b_row_ranges(const LaunchCtx &lc, int k, Csr B, int4 *brange)
+cudaError_t launch_b_row_ranges(const LaunchCtx &lc, int k, int n, Csr B, int4 *brange, Counters *ctr)
 {
     if (k <= 0) return cudaSuccess;
     ++*lc.launches;
-    k_b_row_ranges<<<(k + 255) / 256, 256, 0, lc.stream>>>(k, B.rowptr, B.col, brange);
+    k_b_row_ranges<<<(int)(((long long)k * 8 + 255) / 256), 256, 0, lc.stream>>>(k, n, B.rowptr, B.col, brange, ctr);
     return cudaGetLastError();
 }
 
@@ -40,7 +64,7 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
                                                       const int *__restrict__ rowptrB,
                                                       const int4 *__restrict__ brange, int *__restrict__ prod,
                                                       int *__restrict__ rc, int *__restrict__ rlo,
-                                                      int *__restrict__ rspan, const int max_span,
+                                                      int *__restrict__ rspan, const int max_span, const int k,
                                                       Counters *__restrict__ ctr)
 {
     __shared__ int s_hist[MAX_BINS];
@@ -79,7 +103,12 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
         for (int j0 = 0; j0 < max_na; j0 += G) {
             const int j = j0 + gl;
             if (j < na) {
-                const int4 br = __ldg(brange + colA[a0 + j]);
+                const int ck = colA[a0 + j];
+                if ((unsigned)ck >= (unsigned)k) {   // column of A outside B's rows: reported, not followed
+                    ctr->bad_A = 1;
+                    continue;
+                }
+                const int4 br = __ldg(brange + ck);
                 s += (long long)br.y;
                 lo = min(lo, br.z);
                 hi = max(hi, br.w);
@@ -134,7 +163,7 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
     }
 }
 
-cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr B, const int4 *brange, int *prod,
+cudaError_t launch_row_products(const LaunchCtx &lc, int m, int k, int nnzA, Csr A, Csr B, const int4 *brange, int *prod,
                                 int *rc, int *rlo, int *rspan, Counters *ctr)
 {
     if (m <= 0) return cudaSuccess;
@@ -149,11 +178,11 @@ cudaError_t launch_row_products(const LaunchCtx &lc, int m, int nnzA, Csr A, Csr
     if (blocks > cap) blocks = cap;
     ++*lc.launches;
     switch (G) {
-    case 2: k_row_products<2><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
-    case 4: k_row_products<4><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
-    case 8: k_row_products<8><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
-    case 16: k_row_products<16><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
-    default: k_row_products<32><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, ctr); break;
+    case 2: k_row_products<2><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, k, ctr); break;
+    case 4: k_row_products<4><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, k, ctr); break;
+    case 8: k_row_products<8><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, k, ctr); break;
+    case 16: k_row_products<16><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, k, ctr); break;
+    default: k_row_products<32><<<(int)blocks, threads, 0, lc.stream>>>(m, A.rowptr, A.col, B.rowptr, brange, prod, rc, rlo, rspan, lc.max_span, k, ctr); break;
     }
     return cudaGetLastError();
 }

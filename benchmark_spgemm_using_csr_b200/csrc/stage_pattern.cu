@@ -11,6 +11,10 @@ namespace bhb {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pat_set_insert(PatSet *set, const int d)
 {
+    if (d == PAT_EMPTY) {   // (an offset no int32-indexed matrix of sane size has)
+        set->overflow = 1;
+        return;
+    }
     unsigned h = ((unsigned)d * 2654435761u) >> (32 - 9);
     static_assert(PAT_SET_SLOTS == 512, "hash shift");
     volatile int *vs = set->slot;

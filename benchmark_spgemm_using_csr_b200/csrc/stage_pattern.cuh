@@ -27,7 +27,7 @@ namespace bhb {
 constexpr int PAT_MAX_OFFS = 64;      // distinct diagonals per operand
 constexpr int PAT_MAX_OUT = 256;      // distinct diagonals of C (one byte per lookup)
 constexpr int PAT_SET_SLOTS = 512;    // device hash set (power of two, >> PAT_MAX_OFFS + threads racing past it)
-constexpr int PAT_EMPTY = (int)0x80000000;
+constexpr int PAT_EMPTY = (int)0x80808080;   // what cudaMemset(0x80) leaves in a slot
 
 struct PatSet {
     int count;

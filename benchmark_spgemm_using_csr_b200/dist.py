@@ -75,13 +75,32 @@ class CudaEngine:
         capi.check(self.lib, self.ctx, self.lib.bhb200_create(ctypes.byref(self.ctx), device))
         self.device = device
         self._keep = None
+        # The library must run on a stream that is ordered after the producers of its operands
+        # (torch kernels, NCCL receives) -- not on the context's private non-blocking stream.
+        # Default: torch's current stream; the legacy default stream has handle 0, which
+        # bhb200_set_stream reads as "own stream", so a dedicated torch stream is used then and
+        # set_operands()/spgemm() make it wait for the current stream.
+        cur = torch.cuda.current_stream(device)
+        self._own = None
+        if cur.cuda_stream == 0:
+            self._own = torch.cuda.Stream(device=device)
+            self.use_stream(self._own.cuda_stream)
+        else:
+            self.use_stream(cur.cuda_stream)
 
     def use_stream(self, cuda_stream_ptr: int):
         capi.check(self.lib, self.ctx, self.lib.bhb200_set_stream(self.ctx, ctypes.c_void_p(cuda_stream_ptr)))
+        if self._own is not None and cuda_stream_ptr != self._own.cuda_stream:
+            self._own = None
+
+    def _order_after_producers(self):
+        if self._own is not None:
+            self._own.wait_stream(torch.cuda.current_stream(self.device))
 
     def set_operands(self, m, k, n, A, B):
         """A, B = (rowptr, col, val) torch CUDA tensors (int32, int32, f32/f64)."""
         self._keep = (A, B)
+        self._order_after_producers()
         dtype = capi.DTYPE_F64 if A[2].dtype == torch.float64 else capi.DTYPE_F32
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         capi.check(self.lib, self.ctx, self.lib.bhb200_init_data_device(
@@ -90,11 +109,13 @@ class CudaEngine:
         self.m, self.vdtype = m, A[2].dtype
 
     def spgemm(self) -> int:
+        self._order_after_producers()
         capi.check(self.lib, self.ctx, self.lib.bhb200_spgemm(self.ctx))
         return int(self.lib.bhb200_get_nnzC(self.ctx))
 
     def result(self) -> LocalResult:
-        """Copies of the device-resident result as torch tensors (device to device)."""
+        """Copies of the device-resident result as torch tensors (device to device; the copy is
+        complete on the host when bhb200_copy_C_to_device returns, so any stream may use them)."""
         nnzC = int(self.lib.bhb200_get_nnzC(self.ctx))
         dev = torch.device("cuda", self.device)
         rowptr = torch.empty(self.m + 1, dtype=torch.int64, device=dev)
@@ -104,6 +125,19 @@ class CudaEngine:
             self.ctx, ctypes.c_void_p(rowptr.data_ptr()), ctypes.c_void_p(col.data_ptr()),
             ctypes.c_void_p(val.data_ptr())))
         return LocalResult(nnzC, rowptr, col[:nnzC], val[:nnzC])
+
+    def rowptr64_host(self) -> np.ndarray:
+        out = np.empty(self.m + 1, dtype=np.int64)
+        capi.check(self.lib, self.ctx, self.lib.bhb200_get_rowptrC_i64(self.ctx, ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def get_C_range(self, first: int, count: int):
+        """Entries [first, first+count) of the local C block as host arrays (col int32, val)."""
+        col = np.empty(max(count, 0), dtype=np.int32)
+        val = np.empty(max(count, 0), dtype=np.float64 if self.vdtype == torch.float64 else np.float32)
+        capi.check(self.lib, self.ctx, self.lib.bhb200_get_C_range(
+            self.ctx, int(first), int(count), ctypes.c_void_p(col.ctypes.data), ctypes.c_void_p(val.ctypes.data)))
+        return col, val
 
     def stats(self) -> dict:
         st = capi.Stats()
@@ -181,6 +215,61 @@ class RowBlockSpGEMM:
         else:
             self.A = self._scatter_A(A, root, vt)
         self.engine.set_operands(r1 - r0, meta["k"], meta["n"], self.A, self.B)
+        return self
+
+    def setup_square_from_device_root(self, B_dev, n: int, root: int = 0):
+        """C = B*B with B = (rowptr int32, col int32, val) torch tensors ALREADY ON `root`'s device
+        (None elsewhere), n x n.  Partition on the per-row products (computed on the device),
+        B broadcast with NCCL -- rowptr first --, every rank slices its row block of A out of its
+        copy of B.  Nothing passes through host memory except the few partition boundaries."""
+        dev = self.device
+        if self.rank == root:
+            Brp, Bc, Bv = B_dev
+            lenB = (Brp[1:] - Brp[:-1]).to(torch.int64)
+            csum = torch.zeros(Bc.numel() + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(lenB[Bc.to(torch.int64)], 0, out=csum[1:])
+            rp64 = Brp.to(torch.int64)
+            prods = csum[rp64[1:]] - csum[rp64[:-1]]
+            prefix = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(prods, 0, out=prefix[1:])
+            total = int(prefix[-1].item())
+            targets = torch.tensor([(total * r) // self.world for r in range(1, self.world)], dtype=torch.int64, device=dev)
+            inner = torch.searchsorted(prefix, targets, right=False).clamp(max=n).cpu().numpy() if self.world > 1 else []
+            bounds = np.maximum.accumulate(np.concatenate([[0], np.asarray(inner, dtype=np.int64), [n]]).astype(np.int64))
+            nnz_bounds = [int(x) for x in Brp[torch.from_numpy(bounds).to(dev)].cpu().numpy()]
+            block_products = [int((prefix[int(bounds[r + 1])] - prefix[int(bounds[r])]).item()) for r in range(self.world)]
+            meta = dict(m=n, k=n, n=n, nnzA=int(Bc.numel()), nnzB=int(Bc.numel()), dtype=str(Bv.dtype).replace("torch.", ""),
+                        bounds=bounds.tolist(), nnz_bounds=nnz_bounds, products=total, block_products=block_products,
+                        max_row_products=int(prods.max().item()))
+            del lenB, csum, rp64, prods, prefix
+        else:
+            meta = None
+        if self.world > 1:
+            box = [meta]
+            dist.broadcast_object_list(box, src=root, group=self.group)
+            meta = box[0]
+        self.meta = meta
+        self.bounds = np.asarray(meta["bounds"], dtype=np.int64)
+        vt = torch.float64 if meta["dtype"] == "float64" else torch.float32
+
+        def bcast(t, numel, tdtype):
+            if self.rank != root:
+                t = torch.empty(numel, dtype=tdtype, device=dev)
+            if self.world > 1:
+                dist.broadcast(t, src=root, group=self.group)
+            return t
+
+        t0 = _now(dev)
+        Brp = bcast(B_dev[0] if self.rank == root else None, n + 1, torch.int32)
+        Bc = bcast(B_dev[1] if self.rank == root else None, meta["nnzB"], torch.int32)
+        Bv = bcast(B_dev[2] if self.rank == root else None, meta["nnzB"], vt)
+        self.timings["broadcast_B_s"] = _now(dev) - t0
+        self.B = (Brp, Bc, Bv)
+        r0, r1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        e0, e1 = meta["nnz_bounds"][self.rank], meta["nnz_bounds"][self.rank + 1]
+        Arp = (Brp[r0:r1 + 1] - Brp[r0]).contiguous()
+        self.A = (Arp, Bc[e0:e1], Bv[e0:e1])
+        self.engine.set_operands(r1 - r0, n, n, self.A, self.B)
         return self
 
     def _scatter_A(self, A, root, vt):

@@ -18,7 +18,7 @@ import numpy as np
 
 __all__ = [
     "CSR", "poisson5pt", "poisson9pt", "poisson7pt", "poisson27pt", "rmat",
-    "uniform_rect", "random_csr", "banded_random", "int_values", "real_values", "transpose_pattern",
+    "uniform_rect", "random_csr", "banded_random", "diagonals", "rmat_counter", "rmat_counter_torch", "int_values", "real_values", "transpose_pattern",
 ]
 
 
@@ -241,3 +241,107 @@ def transpose_pattern(A: CSR, value_seed=3, values="int") -> CSR:
     """A^T with fresh values (test helper for rectangular chains)."""
     r = np.repeat(np.arange(A.rows, dtype=np.int64), np.diff(A.rowptr))
     return _from_coo_dedup(A.cols, A.rows, A.col.astype(np.int64), r, value_seed, A.val.dtype, values)
+
+
+def diagonals(rows, cols, offsets, keep=1.0, seed=1, value_seed=2, dtype=np.float64, values="int") -> CSR:
+    """Entries at (i, i + d) for every offset d in `offsets` that lands inside the matrix
+    (DIA-like: stencils, banded and Toeplitz-structured matrices); with keep < 1 each entry
+    survives with that probability, so rows hold irregular subsets of the diagonals."""
+    offs = np.unique(np.asarray(offsets, dtype=np.int64))
+    i = np.repeat(np.arange(rows, dtype=np.int64), offs.size)
+    c = i + np.tile(offs, rows)
+    ok = (c >= 0) & (c < cols)
+    if keep < 1.0:
+        rng = np.random.Generator(np.random.PCG64(seed))
+        ok &= rng.random(ok.size) < keep
+    return _from_coo_dedup(rows, cols, i[ok], c[ok], value_seed, dtype, values)
+
+
+# ---- counter-based R-MAT: the same matrix from numpy (host) and torch (device) -----------------
+# bench.py builds config 5 (scale 24: 2.7e8 edges) on the GPU in seconds; numpy's PCG stream above
+# cannot be reproduced there, so this generator draws every (edge, level) decision from a
+# SplitMix64 hash of its counter.  Bit-identical across the two back ends (tests/test_generators.py).
+_SM_GAMMA = 0x9E3779B97F4A7C15
+_SM_M1 = 0xBF58476D1CE4E5B9
+_SM_M2 = 0x94D049BB133111EB
+_VAL_MUL = 0x632BE59BD9B4E019
+
+
+def _rmat_thresholds(a, b, c, d):
+    if abs(a + b + c + d - 1.0) > 1e-9:
+        raise ValueError("a+b+c+d must be 1")
+    s = float(1 << 32)
+    return int(a * s), int((a + b) * s), int((a + b + c) * s)
+
+
+def rmat_counter(scale, edge_factor=16, a=0.45, b=0.15, c=0.15, d=0.25, seed=1, value_seed=2, dtype=np.float64) -> CSR:
+    """R-MAT like rmat(), decisions from SplitMix64(edge * 64 + level + seed * 2^40) >> 32."""
+    n = 1 << scale
+    E = edge_factor * n
+    ta, tb, tc = _rmat_thresholds(a, b, c, d)
+    e = np.arange(E, dtype=np.uint64) * np.uint64(64) + (np.uint64(seed) << np.uint64(40))
+    r = np.zeros(E, dtype=np.int64)
+    cc = np.zeros(E, dtype=np.int64)
+    with np.errstate(over="ignore"):
+        for level in range(scale):
+            u = (_splitmix64(e + np.uint64(level)) >> np.uint64(32)).astype(np.int64)
+            rbit = u >= tb
+            cbit = ((u >= ta) & (u < tb)) | (u >= tc)
+            r = (r << 1) | rbit
+            cc = (cc << 1) | cbit
+    return _from_coo_dedup(n, n, r, cc, value_seed, dtype, "int")
+
+
+def _i64(x: int) -> int:
+    """The two's-complement int64 holding the uint64 bit pattern x."""
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def rmat_counter_torch(scale, edge_factor=16, a=0.45, b=0.15, c=0.15, d=0.25, seed=1, value_seed=2, dtype=None,
+                       device="cuda"):
+    """rmat_counter() on a torch device.  Returns (rowptr int32, col int32, val) tensors there.
+    int64 arithmetic wraps like uint64; logical shifts are arithmetic shifts + a mask."""
+    import torch
+    dtype = dtype or torch.float64
+    n = 1 << scale
+    E = edge_factor * n
+    ta, tb, tc = _rmat_thresholds(a, b, c, d)
+
+    def lsr(x, s):
+        return (x >> s) & ((1 << (64 - s)) - 1)
+
+    def splitmix(x):
+        x = x + _i64(_SM_GAMMA)
+        x = (x ^ lsr(x, 30)) * _i64(_SM_M1)
+        x = (x ^ lsr(x, 27)) * _i64(_SM_M2)
+        return x ^ lsr(x, 31)
+
+    e = torch.arange(E, dtype=torch.int64, device=device) * 64 + _i64(seed << 40)
+    r = torch.zeros(E, dtype=torch.int64, device=device)
+    cc = torch.zeros(E, dtype=torch.int64, device=device)
+    for level in range(scale):
+        u = lsr(splitmix(e + level), 32)
+        rbit = (u >= tb).to(torch.int64)
+        cbit = (((u >= ta) & (u < tb)) | (u >= tc)).to(torch.int64)
+        r = (r << 1) | rbit
+        cc = (cc << 1) | cbit
+        del u, rbit, cbit
+    del e
+    key = (r << 32) | cc
+    del r, cc
+    key = torch.unique(key)                                   # sorted, duplicate-free
+    rows = key >> 32
+    col = (key & 0xFFFFFFFF).to(torch.int32)
+    del key
+    nnz = int(col.numel())
+    if nnz > np.iinfo(np.int32).max:
+        raise OverflowError("nnz exceeds int32")
+    counts = torch.bincount(rows, minlength=n)
+    del rows
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    torch.cumsum(counts, 0, out=rowptr[1:])
+    h = splitmix(torch.arange(nnz, dtype=torch.int64, device=device) + _i64(value_seed * _VAL_MUL))
+    hi, lo = lsr(h, 32), h & 0xFFFFFFFF
+    val = (((hi * 4 + lo) % 9) + 1).to(dtype)                 # uint64 h mod 9 (2^32 mod 9 = 4)
+    return rowptr.to(torch.int32), col, val

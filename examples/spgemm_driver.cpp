@@ -16,6 +16,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -53,29 +54,68 @@ static Csr stencil(int nx, int ny, int nz, bool box)
     return A;
 }
 
+// MatrixMarket coordinate reader (main.cu:56-64 uses cusp::io::read_matrix_market_file): real /
+// integer / pattern fields, general / symmetric / skew-symmetric; duplicates summed, columns sorted.
+// Returns false (with a message) on anything else or on a malformed file.
 static bool read_mtx(const string &path, Csr &A)
 {
     ifstream f(path);
-    if (!f) return false;
-    string line;
-    getline(f, line);
-    const bool pattern = line.find("pattern") != string::npos;
-    const bool symmetric = line.find("symmetric") != string::npos;
-    while (getline(f, line) && (line.empty() || line[0] == '%')) {}
-    int rows, cols;
-    long nnz;
-    istringstream(line) >> rows >> cols >> nnz;
-    vector<map<int, double>> R(rows);
-    for (long e = 0; e < nnz; e++) {
-        int i, j;
-        double v = 1.0;
-        f >> i >> j;
-        if (!pattern) f >> v;
-        R[i - 1][j - 1] += v;
-        if (symmetric && i != j) R[j - 1][i - 1] += v;
+    if (!f) {
+        cout << "cannot open " << path << endl;
+        return false;
     }
-    A.rows = rows;
-    A.cols = cols;
+    string line, banner, object, format, field, symmetry;
+    getline(f, line);
+    istringstream hdr(line);
+    hdr >> banner >> object >> format >> field >> symmetry;
+    auto lower = [](string &t) { for (auto &ch : t) ch = (char)tolower((unsigned char)ch); };
+    lower(object), lower(format), lower(field), lower(symmetry);
+    if (banner != "%%MatrixMarket" || object != "matrix" || format != "coordinate") {
+        cout << path << ": only MatrixMarket coordinate matrices are supported" << endl;
+        return false;
+    }
+    const bool pattern = field == "pattern";
+    if (!pattern && field != "real" && field != "integer" && field != "double") {
+        cout << path << ": unsupported field '" << field << "'" << endl;
+        return false;
+    }
+    double mirror = 0.0;   // value factor of the mirrored entry; 0 = general
+    if (symmetry == "symmetric") mirror = 1.0;
+    else if (symmetry == "skew-symmetric") mirror = -1.0;
+    else if (symmetry != "general") {
+        cout << path << ": unsupported symmetry '" << symmetry << "'" << endl;
+        return false;
+    }
+    while (getline(f, line) && (line.empty() || line[0] == '%')) {}
+    long rows = 0, cols = 0, nnz = -1;
+    istringstream(line) >> rows >> cols >> nnz;
+    if (rows < 0 || cols < 0 || nnz < 0 || rows > 0x7fffffffL || cols > 0x7fffffffL) {
+        cout << path << ": bad size line" << endl;
+        return false;
+    }
+    vector<map<int, double>> R((size_t)rows);
+    for (long e = 0; e < nnz; e++) {
+        long i = 0, j = 0;
+        double v = 1.0;
+        if (!(f >> i >> j) || (!pattern && !(f >> v))) {
+            cout << path << ": truncated entry list" << endl;
+            return false;
+        }
+        if (i < 1 || i > rows || j < 1 || j > cols) {
+            cout << path << ": entry (" << i << ", " << j << ") outside the matrix" << endl;
+            return false;
+        }
+        R[i - 1][(int)(j - 1)] += v;
+        if (mirror != 0.0 && i != j) {
+            if (j > rows || i > cols) {
+                cout << path << ": symmetric entry outside the matrix" << endl;
+                return false;
+            }
+            R[j - 1][(int)(i - 1)] += mirror * v;
+        }
+    }
+    A.rows = (int)rows;
+    A.cols = (int)cols;
     A.rowptr.assign(1, 0);
     for (auto &r : R) {   // std::map: columns ascending == csr_sort_indices (ref_spgemm.h:37-62)
         for (auto &kv : r) {
@@ -140,7 +180,7 @@ static int run(Csr &A, Csr &B, bool *platforms, int warmups)
     cout << " B: ( " << B.rows << " by " << B.cols << ", nnz = " << B.col.size() << " ) " << endl;
     vector<index_type> rowptrC(A.rows + 1);
     int err = 0;
-    bhsparse *bh_sparse = new bhsparse();   // call sequence of main.cu:104-135
+    std::unique_ptr<bhsparse> bh_sparse(new bhsparse());   // call sequence of main.cu:104-135 (released on every return)
     err = bh_sparse->initPlatform(platforms);
     if (err != BHSPARSE_SUCCESS) return err;
     err = bh_sparse->initData(A.rows, A.cols, B.cols, (int)A.col.size(), A.val.data(), A.rowptr.data(), A.col.data(),
@@ -161,7 +201,6 @@ static int run(Csr &A, Csr &B, bool *platforms, int warmups)
     if (err != BHSPARSE_SUCCESS) return err;
     err = bh_sparse->freePlatform();
     if (err != BHSPARSE_SUCCESS) return err;
-    delete bh_sparse;
     compData(A, B, nnzC, rowptrC.data(), colC.data(), valC.data());
     return BHSPARSE_SUCCESS;
 }

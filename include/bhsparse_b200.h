@@ -81,6 +81,14 @@ typedef struct bhb200_stats {
      * overflowed the speculated capacity and were redone, size of the staging buffer (Ct) */
     int64_t direct_rows, direct_retry_rows, direct_ct_bytes;
     int64_t direct_bin_mask;   /* bit b: symbolic bin b ran in direct mode (its ms_sym_bin is the numeric kernel) */
+    /* diagonal-pattern mode (operands with <= 64 distinct diagonals each, <= 256 in the product):
+     * 1 if the last product ran through it (ms_count then includes the offset sets + codes,
+     * ms_symbolic the mask kernel, ms_numeric the one numeric kernel), and the number of distinct
+     * diagonals of A, B and C and the accumulator length. */
+    int64_t pattern_mode, pattern_nDA, pattern_nDB, pattern_nD, pattern_acc_len;
+    /* host-memory spill: bytes of C / of the staging buffer that live in pinned, device-mapped host
+     * memory because the device could not hold them (0 normally) */
+    int64_t spill_bytes;
 } bhb200_stats;
 
 /* -- platform --------------------------------------------------------------
@@ -108,6 +116,10 @@ BHB200_API int bhb200_init_data_f64(bhb200_ctx *ctx, int m, int k, int n,
 BHB200_API int bhb200_init_data_f32(bhb200_ctx *ctx, int m, int k, int n,
                                     int nnzA, const float *valA, const int32_t *rowptrA, const int32_t *colA,
                                     int nnzB, const float *valB, const int32_t *rowptrB, const int32_t *colB);
+/* 1 if the last bhb200_init_data_{f64,f32} received the SAME host arrays for A and B (C = A*A as
+ * the reference driver's stock workloads set it up, main.cu:32-51): they are uploaded once and both
+ * operands share the device copy.  bhb200_update_values_* then takes one set of values. */
+BHB200_API int bhb200_operands_aliased(const bhb200_ctx *ctx);
 /* Same, but the six arrays are DEVICE pointers on the context's device and are
  * borrowed (not copied, not freed) until bhb200_free_mem: the device-resident
  * operand API of SURVEY.md 8(f).3, used by the multi-GPU row-block driver. */

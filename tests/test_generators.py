@@ -65,3 +65,17 @@ def test_mtx_reader(tmp_path):
     q.write_text("%%MatrixMarket matrix coordinate pattern general\n2 3 2\n1 3\n2 1\n")
     B = read_mtx(str(q))
     assert B.cols == 3 and B.col.tolist() == [2, 0] and B.val.tolist() == [1.0, 1.0]
+
+
+def test_rmat_counter_is_identical_in_numpy_and_torch():
+    """bench.py generates config 5 (R-MAT scale 24) on the GPU with torch; the CPU side (oracle,
+    tests) must see the same matrix from numpy."""
+    for scale, ef in ((6, 4), (11, 16)):
+        A = gen.rmat_counter(scale, ef, seed=3, value_seed=4)
+        rp, col, val = gen.rmat_counter_torch(scale, ef, seed=3, value_seed=4, device="cpu")
+        assert np.array_equal(A.rowptr, rp.numpy()) and np.array_equal(A.col, col.numpy())
+        assert np.array_equal(A.val, val.numpy())
+        assert (np.diff(A.rowptr) >= 0).all() and A.rowptr[-1] == A.col.size
+        for i in range(0, A.rows, 97):
+            c = A.col[A.rowptr[i]:A.rowptr[i + 1]]
+            assert (np.diff(c) > 0).all()

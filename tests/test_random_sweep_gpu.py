@@ -11,6 +11,15 @@ from conftest import assert_csr_equal
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["general", "default"])
+def _path(request, monkeypatch):
+    """Every test of this module runs twice: with the diagonal-pattern mode switched off (the
+    general hash / ESC / range / bitmap kernels these tests were written for) and with the
+    library's default (structured operands then take csrc/stage_pattern.cuh)."""
+    if request.param == "general":
+        monkeypatch.setenv("BHB200_PATTERN", "off")
+
+
 def _row_lengths(rng, rows, cols, kind):
     if kind == 0:
         ln = np.full(rows, int(rng.integers(1, 12)))

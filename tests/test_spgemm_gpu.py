@@ -4,6 +4,8 @@ bit-exact for the integer-valued inputs the reference driver uses (main.cu:82,93
 <= 1e-12 relative (double) / 1e-5 (float) for real-valued inputs -- the tolerances
 BASELINE.json's north_star states (the reference itself only checks 10 %,
 ref_spgemm.h:110)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,6 +16,15 @@ from benchmark_spgemm_using_csr_b200.generators import CSR
 from conftest import assert_csr_equal
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["general", "default"])
+def _path(request, monkeypatch):
+    """Every test of this module runs twice: with the diagonal-pattern mode switched off (the
+    general hash / ESC / range / bitmap kernels these tests were written for) and with the
+    library's default (structured operands then take csrc/stage_pattern.cuh)."""
+    if request.param == "general":
+        monkeypatch.setenv("BHB200_PATTERN", "off")
 
 RTOL = {np.float64: 1e-12, np.float32: 1e-5}
 
@@ -142,6 +153,8 @@ def test_range_kernels_large_span(dt, monkeypatch):
     """27-point rows on a 128x128 plane span 66 053 columns -> RANGE_L bins (config 2's rows).
     These bins are off by default (measured slower than the hash kernels at that span,
     DESIGN.md); BHB200_RANGE=all switches them on."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
     monkeypatch.setenv("BHB200_RANGE", "all")
     A = gen.poisson27pt(128, 128, 6, dtype=dt)
     st = _check(A, A, f"27pt 128x128x6 {dt.__name__}")
@@ -153,6 +166,8 @@ def test_range_kernels_irregular_band(dt, monkeypatch):
     """Irregular banded operands: B rows longer than a warp (tail loop), nnz(C_i) on both
     sides of the 128 / 512 accumulator limits, rows that leave the range path for the hash
     kernels after a range symbolic pass."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
     monkeypatch.setenv("BHB200_RANGE", "all")
     for n, hb, k, what in ((3000, 300, 40, "span<12K c~500"), (6000, 3000, 70, "span~12K c>512"),
                            (20000, 9000, 9, "large span c<=128"), (20000, 9000, 12, "large span c<=512"),
@@ -164,6 +179,8 @@ def test_range_kernels_irregular_band(dt, monkeypatch):
 
 def test_range_kernels_pool_overflow_fallback(monkeypatch):
     """Word-list pool too small: the numeric range kernel must mark those rows itself."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
     monkeypatch.setenv("BHB200_RANGE", "all")
     monkeypatch.setenv("BHB200_DEBUG_WORDLIST_CAP", "1000")
     A = gen.poisson27pt(40, 40, 8)
@@ -179,6 +196,8 @@ def test_range_kernels_pool_overflow_fallback(monkeypatch):
 def test_direct_mode_speculation_holds(dt, monkeypatch):
     """27-point rows: 729 products -> at most 125 outputs; the sampled bound holds for every
     row, no symbolic pass runs for them and nothing is retried."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
     monkeypatch.setenv("BHB200_RANGE", "off")      # (narrow-span rows would take the bitmap kernels instead)
     A = gen.poisson27pt(40, 40, 40, dtype=dt)
     st = _check(A, A, f"27pt 40^3 direct {dt.__name__}")
@@ -191,6 +210,8 @@ def test_direct_mode_speculation_holds(dt, monkeypatch):
 def test_direct_mode_overflow_is_retried(dt, cap, monkeypatch):
     """Force a speculated capacity that is too small for most rows: every row that does not
     fit must be detected and redone by the two-pass path, bit for bit."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
     monkeypatch.setenv("BHB200_DEBUG_FORCE_CAP", cap)
     monkeypatch.setenv("BHB200_RANGE", "off")
     A = gen.poisson27pt(24, 24, 24, dtype=dt)
@@ -210,6 +231,8 @@ def test_direct_mode_wide_bins(dt, monkeypatch):
     """Rows that barely compress (wide random column space): the sampled mean nnz(C_i) is close
     to the product bound, so the bins up to 6144 products run single-pass with the capacity the
     bound dictates (group kernel for 256, CTA kernels for 512..8192) and skip the symbolic pass."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
     per_row = np.array([12, 24, 48, 96, 150, 250, 400])[np.arange(7 * 4500) % 7]
     A = gen.random_csr(7 * 4500, 20000, per_row, seed=41, dtype=dt)
     B = gen.random_csr(20000, 3_000_000, 12, seed=42, value_seed=43, dtype=dt)
@@ -224,6 +247,8 @@ def test_direct_mode_wide_bins(dt, monkeypatch):
 
 
 def test_direct_mode_off_matches(monkeypatch):
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
     monkeypatch.setenv("BHB200_DIRECT", "off")
     monkeypatch.setenv("BHB200_RANGE", "off")
     A = gen.poisson27pt(30, 30, 30)
@@ -290,6 +315,8 @@ def test_wide_column_space():
 def test_repeated_calls_and_reinit():
     """spgemm() twice on one initData (undefined in the reference, counters are
     never reset: bhsparse.h:379-380) and re-initialisation on one context."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
     platforms = [False] * NUM_PLATFORMS
     platforms[BHSPARSE_CUDA] = True
     bh = bhsparse()
@@ -326,3 +353,62 @@ def test_error_paths():
                        np.zeros(A.rows + 1, np.int32)) == capi.ERR_INVALID
     assert "rowptrA" in bh.last_error()
     assert bh.freePlatform() == 0
+
+
+def test_operand_preconditions_are_checked():
+    """Rows of B must be sorted, duplicate-free and inside [0, n); columns of A inside [0, k)
+    (include/bhsparse_b200.h).  The reference silently assumes it (bhsparse_cuda.h:1730,1762);
+    here a violation is an error code, never corrupted memory or lost contributions."""
+    platforms = [False] * NUM_PLATFORMS
+    platforms[BHSPARSE_CUDA] = True
+    A = gen.random_csr(300, 200, 9, seed=3)
+    B = gen.random_csr(200, 400, 12, seed=4, value_seed=5)
+
+    def run(A, B):
+        bh = bhsparse()
+        assert bh.initPlatform(platforms) == 0
+        err = bh.initData(A.rows, A.cols, B.cols, A.nnz, A.val, A.rowptr, A.col, B.nnz, B.val, B.rowptr, B.col,
+                          np.zeros(A.rows + 1, np.int32))
+        if err == 0:
+            err = bh.spgemm()
+        msg = bh.last_error()
+        bh.freePlatform()
+        return err, msg
+
+    assert run(A, B)[0] == 0
+    c = B.col.copy()
+    s = B.rowptr[57]
+    c[s], c[s + 1] = c[s + 1], c[s]                       # one unsorted pair
+    err, msg = run(A, CSR(B.rows, B.cols, B.rowptr, c, B.val))
+    assert err == capi.ERR_INVALID and "sorted" in msg
+    c = B.col.copy()
+    c[B.rowptr[120] + 3] = c[B.rowptr[120] + 2]           # a duplicate column
+    assert run(A, CSR(B.rows, B.cols, B.rowptr, c, B.val))[0] == capi.ERR_INVALID
+    c = B.col.copy()
+    c[B.rowptr[199 + 1] - 1] = B.cols                     # column == n
+    assert run(A, CSR(B.rows, B.cols, B.rowptr, c, B.val))[0] == capi.ERR_INVALID
+    ca = A.col.copy()
+    ca[A.rowptr[10]] = -1                                 # column of A outside [0, k)
+    err, msg = run(CSR(A.rows, A.cols, A.rowptr, ca, A.val), B)
+    assert err == capi.ERR_INVALID and "A" in msg
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_host_memory_spill(dt, monkeypatch):
+    """SURVEY.md 8f-4 (the reference's OpenCL `-opencl-hcmp` mode, bhsparse_opencl.cpp:219-227,
+    832-863): when the device cannot hold C or the staging buffer they live in pinned, device-mapped
+    host memory.  Forced here by a debug cap on the size of a single device buffer."""
+    monkeypatch.setenv("BHB200_DEBUG_DEVICE_CAP", "65536")
+    A = gen.poisson27pt(16, 16, 16, dtype=dt)              # pattern mode or direct mode + staging
+    rp, col, val, st = spgemm(A, A, return_stats=True)
+    assert st["spill_bytes"] >= (4 + A.val.itemsize) * st["nnzC"]
+    assert_csr_equal((rp, col, val), _oracle(A, A), what="spill stencil")
+    R = gen.rmat(12, 16, a=0.57, b=0.19, c=0.19, d=0.05, dtype=dt)     # hash / CTA / global-bitmap bins
+    rp, col, val, st = spgemm(R, R, return_stats=True)
+    assert st["spill_bytes"] > 0
+    assert_csr_equal((rp, col, val), _oracle(R, R), what="spill rmat")
+    # rows beyond the on-chip tables: global bitmap-rank kernel, red.global.add into the spilled C
+    L = gen.random_csr(6, 120000, np.array([40000, 3, 9000, 0, 20000, 17]), seed=9, dtype=dt)
+    rp, col, val, st = spgemm(L, _identity(120000, dt), return_stats=True)
+    assert st["spill_bytes"] > 0 and st["num_bin_rows"][12] > 0
+    assert_csr_equal((rp, col, val), _oracle(L, _identity(120000, dt)), what="spill large rows")
