@@ -28,10 +28,11 @@ SOURCES = [
     "stage_range.cu",
     "stage_pattern.cu",
     "pattern_plan.cu",
+    "dist_nccl.cu",
     "stage_numeric_f32.cu",
     "stage_numeric_f64.cu",
 ]
-HEADERS = ["common.cuh", "stage_numeric.cuh", "stage_range.cuh", "stage_range_vec.cuh", "stage_pattern.cuh", "pattern_plan.h", os.path.join(INCLUDE, "bhsparse_b200.h")]
+HEADERS = ["common.cuh", "stage_numeric.cuh", "stage_range.cuh", "stage_range_vec.cuh", "stage_pattern.cuh", "pattern_plan.h", "context.h", os.path.join(INCLUDE, "bhsparse_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -94,7 +95,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [cc] + ccbin + ["-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [cc] + ccbin + ["-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -36,7 +36,11 @@ EXPORTED = [
     "bhb200_get_C_f32", "bhb200_get_rowptrC_i64", "bhb200_get_C_range", "bhb200_get_C_device", "bhb200_copy_C_to_device", "bhb200_get_row_products",
     "bhb200_get_stats", "bhb200_set_profiling", "bhb200_free_mem", "bhb200_version",
     "bhb200_update_values_f64", "bhb200_update_values_f32", "bhb200_spgemm_numeric",
+    "bhb200_dist_unique_id", "bhb200_dist_init", "bhb200_dist_setup_square", "bhb200_dist_spgemm",
+    "bhb200_dist_get_layout", "bhb200_dist_get_block_products", "bhb200_dist_get_global_rowptr_device",
+    "bhb200_dist_broadcast_ms", "bhb200_dist_finalize",
 ]
+DIST_ID_BYTES = 128
 
 
 class Stats(ctypes.Structure):
@@ -123,6 +127,15 @@ def load(build_if_missing: bool = False):
     L.bhb200_get_stats.argtypes = [ctxp, POINTER(Stats)]
     L.bhb200_set_profiling.argtypes = [ctxp, c_int]
     L.bhb200_free_mem.argtypes = [ctxp]
+    L.bhb200_dist_unique_id.argtypes = [c_void_p]
+    L.bhb200_dist_init.argtypes = [ctxp, c_int, c_int, c_void_p]
+    L.bhb200_dist_setup_square.argtypes = [ctxp, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]
+    L.bhb200_dist_spgemm.argtypes = [ctxp]
+    L.bhb200_dist_get_layout.argtypes = [ctxp] + [POINTER(c_int64)] * 5
+    L.bhb200_dist_get_block_products.argtypes = [ctxp, POINTER(c_int64)]
+    L.bhb200_dist_get_global_rowptr_device.argtypes = [ctxp, POINTER(c_void_p)]
+    L.bhb200_dist_broadcast_ms.argtypes = [ctxp, POINTER(c_float)]
+    L.bhb200_dist_finalize.argtypes = [ctxp]
     for name in EXPORTED:
         f = getattr(L, name)
         if f.restype is c_int:  # default

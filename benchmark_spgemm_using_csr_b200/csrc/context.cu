@@ -4,9 +4,7 @@
 // 2783-2811, 3006-3020).  Host <-> device traffic inside one spgemm call: two reads of a
 // 300-byte counter block (bin sizes; nnz(C)) -- the reference has >= 8 blocking copies of
 // O(m) data plus 3 per merge round.
-#include "../../include/bhsparse_b200.h"
-#include "common.cuh"
-#include "pattern_plan.h"
+#include "context.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -15,128 +13,6 @@
 #include <string>
 
 using namespace bhb;
-
-namespace {
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    bool host = false;   // spilled: pinned, device-mapped HOST memory (see reserve_spillable)
-    void drop(size_t *total)
-    {
-        if (p) {
-            if (host) cudaFreeHost(p);
-            else cudaFree(p);
-            *total -= cap;
-        }
-        p = nullptr;
-        cap = 0;
-        host = false;
-    }
-    cudaError_t reserve(size_t bytes, size_t *total)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        drop(total);
-        // round up to 256 B; grow-only cache, released by free_mem
-        size_t want = (bytes + 255) & ~(size_t)255;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return e;
-        }
-        cap = want;
-        *total += cap;
-        return cudaSuccess;
-    }
-    // Host-memory spill (the reference's OpenCL build keeps Ct in host-coherent
-    // "re-allocatable" memory for the same reason, SpGEMM_opencl/bhsparse_opencl.cpp:219-227,
-    // 441-454, 832-863): if the device cannot hold the buffer -- cudaMalloc fails, or the request
-    // exceeds `device_cap` (BHB200_DEBUG_DEVICE_CAP, tests) -- it is placed in pinned host memory
-    // mapped into the device address space; kernels then write it across NVLink-C2C / PCIe.
-    cudaError_t reserve_spillable(size_t bytes, size_t *total, size_t device_cap, bool *spilled)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        cudaError_t e = cudaErrorMemoryAllocation;
-        if (bytes <= device_cap) e = reserve(bytes, total);
-        if (e == cudaSuccess) return e;
-        cudaGetLastError();
-        drop(total);
-        size_t want = (bytes + 4095) & ~(size_t)4095;
-        e = cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return e;
-        }
-        cap = want;
-        host = true;
-        *total += cap;
-        if (spilled) *spilled = true;
-        return cudaSuccess;
-    }
-    void release(size_t *total) { drop(total); }
-    template <typename T>
-    T *as() const
-    {
-        return reinterpret_cast<T *>(p);
-    }
-};
-
-}  // namespace
-
-struct bhb200_ctx {
-    int device = 0;
-    int sm_count = 0;
-    char name[256] = {0};
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    std::string err;
-
-    // operands
-    bool have_data = false;
-    bool borrowed = false;
-    bool aliased = false;   // host API: A and B were the same host arrays, uploaded once
-    int dtype = BHB200_DTYPE_F64;
-    int m = 0, k = 0, n = 0, nnzA = 0, nnzB = 0;
-    DevBuf a_rowptr, a_col, a_val, b_rowptr, b_col, b_val;
-    Csr A{nullptr, nullptr, nullptr}, B{nullptr, nullptr, nullptr};
-
-    // workspace (grow-only, reused across calls)
-    DevBuf prod, rc, queue, rowoff64, rowptr32, blocksums, counters, bitmap, prefix;
-    DevBuf brange, rlo, rspan, wl_off, wl_cnt, wl_idx, wl_bits;   // span info + word-list pool (range kernels)
-    DevBuf ct_off, ct_col, ct_val, retry_q;                       // direct mode: staging buffer (Ct) + retry queues
-    // diagonal-pattern mode (stage_pattern.cuh): offset sets, per-entry codes, masks, tables
-    DevBuf pat_sets, pat_ta, pat_tb, pat_maskB, pat_outmask, pat_tables;
-    PatSet *h_sets = nullptr;    // pinned, [2]
-    PatternPlan plan;
-    size_t device_cap = ~(size_t)0;   // BHB200_DEBUG_DEVICE_CAP: largest single buffer the device may hold (tests)
-    int pattern_enable = 1;      // BHB200_PATTERN=off disables
-    bool last_pattern = false;   // the last product ran in pattern mode
-    PatTables last_tables{};
-    const unsigned char *last_ta = nullptr, *last_tb = nullptr;
-    int direct_mode = 1;                                          // BHB200_DIRECT=off disables
-    int direct_wide = 1;                                          // BHB200_DIRECT=tight: speculated capacities <= 128 only
-    size_t bitmap_zeroed_bytes = 0;
-    DevBuf colC, valC;
-    Counters *h_ctr = nullptr;   // pinned
-    size_t dev_bytes = 0;
-
-    bool have_C = false;
-    int64_t nnzC = 0;
-    // structure reuse (bhb200_spgemm_numeric): what the last full product left behind
-    int last_G = 32;
-    WordLists last_wl{nullptr, nullptr, nullptr, nullptr, 0};
-    bool reuse_bins_valid = false;   // queue holds the numeric bins without the copy bin
-    int reuse_num_bin[MAX_BINS] = {0};
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool timing_valid = false;
-    bool profiling = false;
-    int max_span = SPAN_SMALL;   // BHB200_RANGE=off|small|all overrides (experiments)
-    // per-launch events: [0] symbolic, [1] numeric; one before each bin + one after the last
-    cudaEvent_t ev_bin[2][MAX_BINS + 1] = {};
-    bool ev_bin_used[2][MAX_BINS + 1] = {};
-    int launches = 0;
-    bhb200_stats stats;
-};
 
 namespace {
 
@@ -209,14 +85,14 @@ int init_host(bhb200_ctx *ctx, int dtype, int m, int k, int n, int nnzA, const v
     const size_t vs = vsize(dtype);
     CU(ctx->a_rowptr.reserve((size_t)(m + 1) * 4, &ctx->dev_bytes), "alloc rowptrA");
     CU(ctx->a_col.reserve((size_t)nnzA * 4 + 4, &ctx->dev_bytes), "alloc colA");
-    CU(ctx->a_val.reserve((size_t)nnzA * vs + 8, &ctx->dev_bytes), "alloc valA");
+    CU(ctx->a_val.reserve((size_t)nnzA * vs + 16, &ctx->dev_bytes), "alloc valA");
     // C = A*A with the SAME host arrays passed twice (the reference driver's stock workloads build
     // A and B identically, main.cu:32-51): one upload, both operands point at it
     const bool alias = m == k && nnzA == nnzB && rowptrA == rowptrB && colA == colB && valA == valB;
     if (!alias) {
         CU(ctx->b_rowptr.reserve((size_t)(k + 1) * 4, &ctx->dev_bytes), "alloc rowptrB");
         CU(ctx->b_col.reserve((size_t)nnzB * 4 + 4, &ctx->dev_bytes), "alloc colB");
-        CU(ctx->b_val.reserve((size_t)nnzB * vs + 8, &ctx->dev_bytes), "alloc valB");
+        CU(ctx->b_val.reserve((size_t)nnzB * vs + 16, &ctx->dev_bytes), "alloc valB");
     }
     cudaStream_t s = ctx->stream;
     CU(cudaMemcpyAsync(ctx->a_rowptr.p, rowptrA, (size_t)(m + 1) * 4, cudaMemcpyHostToDevice, s), "H2D rowptrA");
@@ -442,13 +318,20 @@ int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab)
     const PatTables t = pattern_tables(plan, ctx->pat_tables.as<unsigned char>());
     unsigned char *tb = ctx->pat_tb.as<unsigned char>();
     unsigned char *ta = same_ab ? tb : ctx->pat_ta.as<unsigned char>();
-    CU(launch_pat_codes(lc, ctx->k, ctx->B.rowptr, ctx->B.col, t.offsB, t.nDB, tb, ctx->pat_maskB.as<unsigned long long>()),
-       "pattern codes of B");
-    if (!same_ab) CU(launch_pat_codes(lc, ctx->m, ctx->A.rowptr, ctx->A.col, t.offsA, t.nDA, ta, nullptr), "pattern codes of A");
-    CU(cudaEventRecord(ctx->ev[1], s), "event");
     int *rcnt = ctx->rc.as<int>();
     Counters *d_ctr = ctx->counters.as<Counters>();
-    CU(launch_pat_symbolic(lc, ctx->m, ctx->A, ta, ctx->pat_maskB.as<unsigned long long>(), t, ctx->pat_outmask.as<unsigned>(), rcnt),
+    const long long spanA = (long long)plan.DA.back() - plan.DA.front() + 1, spanB = (long long)plan.DB.back() - plan.DB.front() + 1;
+    CU(launch_pat_codes(lc, ctx->k, ctx->n, ctx->B.rowptr, ctx->B.col, t.offsB, t.nDB, spanB, tb, ctx->pat_maskB.as<unsigned long long>(),
+                        &d_ctr->bad_B),
+       "pattern codes of B");
+    if (!same_ab)
+        CU(launch_pat_codes(lc, ctx->m, ctx->k, ctx->A.rowptr, ctx->A.col, t.offsA, t.nDA, spanA, ta, nullptr, &d_ctr->bad_A),
+           "pattern codes of A");
+    CU(cudaEventRecord(ctx->ev[1], s), "event");
+    // exact nnz(C_i) from the offset masks; also the per-row product counts (compute_nnzCt,
+    // bhsparse_cuda.h:210-237) and their total -- the general path's stage-1 kernels are not run
+    CU(launch_pat_symbolic(lc, ctx->m, ctx->A, ta, ctx->pat_maskB.as<unsigned long long>(), t, ctx->pat_outmask.as<unsigned>(), rcnt,
+                           ctx->prod.as<int>(), d_ctr, ctx->k, (double)ctx->nnzA / (double)ctx->m),
        "pattern symbolic");
     CU(cudaEventRecord(ctx->ev[2], s), "event");
     memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
@@ -457,8 +340,12 @@ int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab)
        "row pointer scan");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
     CU(cudaStreamSynchronize(s), "pattern symbolic / scan");
+    if (ctx->h_ctr->bad_B) return fail(ctx, BHB200_ERR_INVALID, "rows of B must be sorted by column, duplicate-free and inside [0, n)");
+    if (ctx->h_ctr->bad_A) return fail(ctx, BHB200_ERR_INVALID, "a column index of A is outside [0, k)");
     ctx->nnzC = (int64_t)ctx->h_ctr->nnzC;
     st.nnzC = ctx->nnzC;
+    st.products = (int64_t)ctx->h_ctr->products;
+    st.max_row_products = ctx->h_ctr->max_row_products;
     {
         bool spilled = false;
         CU(ctx->colC.reserve_spillable((size_t)ctx->nnzC * 4 + 16, &ctx->dev_bytes, ctx->device_cap, &spilled), "alloc colC");
@@ -580,6 +467,7 @@ int bhb200_free_mem(bhb200_ctx *ctx)
 int bhb200_destroy(bhb200_ctx *ctx)
 {
     if (!ctx) return BHB200_ERR_INVALID;
+    bhb200_dist_finalize(ctx);
     bhb200_free_mem(ctx);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
@@ -711,11 +599,20 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     }
     if (try_pattern) {
         PatSet *sets = ctx->pat_sets.as<PatSet>();
-        CU(cudaMemsetAsync(sets, 0x80, 2 * sizeof(PatSet), s), "init offset sets");   // slots = PAT_EMPTY-like filler
+        CU(cudaMemsetAsync(sets, 0x80, 2 * sizeof(PatSet), s), "init offset sets");   // slots = PAT_EMPTY
         CU(cudaMemsetAsync(&sets[0], 0, 8, s), "init offset sets");
         CU(cudaMemsetAsync(&sets[1], 0, 8, s), "init offset sets");
         CU(launch_offset_set(lc, ctx->k, ctx->B.rowptr, ctx->B.col, &sets[1]), "offset set of B");
         if (!same_ab) CU(launch_offset_set(lc, ctx->m, ctx->A.rowptr, ctx->A.col, &sets[0]), "offset set of A");
+        CU(cudaMemcpyAsync(ctx->h_sets, ctx->pat_sets.p, 2 * sizeof(PatSet), cudaMemcpyDeviceToHost, s), "D2H offset sets");
+        CU(cudaStreamSynchronize(s), "offset sets");
+        if (ctx->wait_before_values) {
+            // multi-GPU set-up: the broadcast of B's values overlapped the detection; the rest reads them
+            CU(cudaStreamWaitEvent(s, ctx->wait_before_values, 0), "wait for the broadcast of B's values");
+            ctx->wait_before_values = nullptr;
+        }
+        rc = run_pattern(ctx, lc, same_ab);
+        if (rc != PATTERN_NOT_APPLICABLE) return rc;
     }
     int *rlo = ctx->rlo.as<int>();
     int *rspan = ctx->rspan.as<int>();
@@ -723,8 +620,6 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(launch_row_products(lc, ctx->m, ctx->k, ctx->nnzA, ctx->A, ctx->B, ctx->brange.as<int4>(), prod, rcnt, rlo, rspan, d_ctr),
        "row products kernel");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
-    if (try_pattern)
-        CU(cudaMemcpyAsync(ctx->h_sets, ctx->pat_sets.p, 2 * sizeof(PatSet), cudaMemcpyDeviceToHost, s), "D2H offset sets");
     CU(cudaStreamSynchronize(s), "stage 1");
     Counters hc = *ctx->h_ctr;
     if (hc.bad_B) return fail(ctx, BHB200_ERR_INVALID, "rows of B must be sorted by column, duplicate-free and inside [0, n)");
@@ -733,9 +628,10 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     st.products = (int64_t)hc.products;
     st.max_row_products = hc.max_row_products;
     for (int b = 0; b < BHB200_NUM_SYM_BINS && b < MAX_BINS; ++b) st.sym_bin_rows[b] = hc.sym_bin[b];
-    if (try_pattern) {
-        rc = run_pattern(ctx, lc, same_ab);
-        if (rc != PATTERN_NOT_APPLICABLE) return rc;
+    if (ctx->wait_before_values) {
+        // multi-GPU set-up: the broadcast of B's values overlapped stage 1; everything below reads them
+        CU(cudaStreamWaitEvent(s, ctx->wait_before_values, 0), "wait for the broadcast of B's values");
+        ctx->wait_before_values = nullptr;
     }
     // lanes per row group: follow the average length of the B rows actually referenced
     const double avg_b = ctx->nnzA > 0 ? (double)hc.products / (double)ctx->nnzA : 0.0;

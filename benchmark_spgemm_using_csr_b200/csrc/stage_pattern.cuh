@@ -50,10 +50,12 @@ struct PatTables {
 
 // launchers (stage_pattern.cu)
 cudaError_t launch_offset_set(const LaunchCtx &lc, int rows, const int *rowptr, const int *col, PatSet *set);
-cudaError_t launch_pat_codes(const LaunchCtx &lc, int rows, const int *rowptr, const int *col, const int *offs, int noffs,
-                             unsigned char *code, unsigned long long *rowmask);
+// bad: set to 1 if a column is outside [0, ncols) or (rowmask != nullptr) a row is not strictly ascending
+// span = largest - smallest offset + 1 (a small span selects the direct-table kernel)
+cudaError_t launch_pat_codes(const LaunchCtx &lc, int rows, int ncols, const int *rowptr, const int *col, const int *offs,
+                             int noffs, long long span, unsigned char *code, unsigned long long *rowmask, int *bad);
 cudaError_t launch_pat_symbolic(const LaunchCtx &lc, int m, Csr A, const unsigned char *ta, const unsigned long long *maskB,
-                                PatTables t, unsigned *outmask, int *rc);
+                                PatTables t, unsigned *outmask, int *rc, int *prod, Counters *ctr, int k, double avg_row);
 cudaError_t launch_pat_numeric(const LaunchCtx &lc, int dtype, int m, Csr A, Csr B, const unsigned char *ta,
                                const unsigned char *tb, PatTables t, const unsigned *outmask, const int64_t *rowoff,
                                int *colC, void *valC);

@@ -209,7 +209,9 @@ class RowBlockSpGEMM:
 
         r0, r1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
         e0, e1 = meta["nnz_bounds"][self.rank], meta["nnz_bounds"][self.rank + 1]
-        if a_equals_b:
+        if a_equals_b and self.world == 1:
+            self.A = self.B                    # one rank: A IS B (same arrays: the library sees C = B*B)
+        elif a_equals_b:
             Arp = (Brp[r0:r1 + 1] - Brp[r0]).contiguous()
             self.A = (Arp, Bc[e0:e1], Bv[e0:e1])
         else:
@@ -267,8 +269,11 @@ class RowBlockSpGEMM:
         self.B = (Brp, Bc, Bv)
         r0, r1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
         e0, e1 = meta["nnz_bounds"][self.rank], meta["nnz_bounds"][self.rank + 1]
-        Arp = (Brp[r0:r1 + 1] - Brp[r0]).contiguous()
-        self.A = (Arp, Bc[e0:e1], Bv[e0:e1])
+        if self.world == 1:
+            self.A = self.B                    # one rank: A IS B (same arrays: the library sees C = B*B)
+        else:
+            Arp = (Brp[r0:r1 + 1] - Brp[r0]).contiguous()
+            self.A = (Arp, Bc[e0:e1], Bv[e0:e1])
         self.engine.set_operands(r1 - r0, n, n, self.A, self.B)
         return self
 
@@ -350,3 +355,85 @@ def _now(device) -> float:
     if device.type == "cuda":
         torch.cuda.synchronize(device)
     return time.perf_counter()
+
+
+class NcclRowBlockSpGEMM:
+    """C = B*B across the ranks THROUGH THE C-ABI (bhb200_dist_*, csrc/dist_nccl.cu): partition,
+    NCCL broadcast of B, per-step all-gather of nnz(C) and the global row pointers all happen inside
+    the library; torch.distributed only carries the 128-byte NCCL id to the ranks.  Same interface
+    as RowBlockSpGEMM where bench.py and the tests need it."""
+
+    def __init__(self, engine: CudaEngine, device: torch.device, group=None):
+        self.engine, self.device, self.group = engine, device, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.meta, self.timings, self._keep = None, {}, None
+        lib, ctx = engine.lib, engine.ctx
+        uid = ctypes.create_string_buffer(capi.DIST_ID_BYTES)
+        if self.rank == 0:
+            capi.check(lib, ctx, lib.bhb200_dist_unique_id(uid))
+        if self.world > 1:
+            box = [uid.raw]
+            dist.broadcast_object_list(box, src=0, group=group)
+            uid = ctypes.create_string_buffer(box[0], capi.DIST_ID_BYTES)
+        capi.check(lib, ctx, lib.bhb200_dist_init(ctx, self.rank, self.world, uid))
+
+    def setup_square_from_device_root(self, B_dev, n: int, root: int = 0):
+        lib, ctx = self.engine.lib, self.engine.ctx
+        self.engine._order_after_producers()
+        info = [None]
+        if self.rank == root:
+            Brp, Bc, Bv = B_dev
+            self._keep = B_dev
+            info = [(int(Bc.numel()), str(Bv.dtype).replace("torch.", ""))]
+        if self.world > 1:
+            dist.broadcast_object_list(info, src=root, group=self.group)
+        nnz, dname = info[0]
+        dtype = capi.DTYPE_F64 if dname == "float64" else capi.DTYPE_F32
+        p = (lambda t: ctypes.c_void_p(t.data_ptr())) if self.rank == root else (lambda t: None)
+        capi.check(lib, ctx, lib.bhb200_dist_setup_square(
+            ctx, root, dtype, n, nnz, p(B_dev[0] if B_dev else None), p(B_dev[1] if B_dev else None),
+            p(B_dev[2] if B_dev else None)))
+        ms = ctypes.c_float(0)
+        capi.check(lib, ctx, lib.bhb200_dist_broadcast_ms(ctx, ctypes.byref(ms)))
+        self.timings["broadcast_B_s"] = ms.value * 1e-3
+        r0, r1, ptot = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        capi.check(lib, ctx, lib.bhb200_dist_get_layout(ctx, ctypes.byref(r0), ctypes.byref(r1), None, None, ctypes.byref(ptot)))
+        bp = (ctypes.c_int64 * self.world)()
+        capi.check(lib, ctx, lib.bhb200_dist_get_block_products(ctx, bp))
+        self.rows = (int(r0.value), int(r1.value))
+        self.engine.m = self.rows[1] - self.rows[0]
+        self.engine.vdtype = torch.float64 if dtype == capi.DTYPE_F64 else torch.float32
+        self.meta = dict(m=n, k=n, n=n, nnzA=nnz, nnzB=nnz, dtype=dname, products=int(ptot.value),
+                         block_products=[int(x) for x in bp])
+        return self
+
+    def spgemm(self):
+        """Returns (nnzC_local, None, None): offsets and totals stay on the device; layout() reads them."""
+        lib, ctx = self.engine.lib, self.engine.ctx
+        self.engine._order_after_producers()
+        capi.check(lib, ctx, lib.bhb200_dist_spgemm(ctx))
+        return int(lib.bhb200_get_nnzC(ctx)), None, None
+
+    def layout(self):
+        """(row_begin, row_end, nnz_offset, nnz_total) of this rank -- copies nranks int64 from the device."""
+        lib, ctx = self.engine.lib, self.engine.ctx
+        v = [ctypes.c_int64() for _ in range(4)]
+        capi.check(lib, ctx, lib.bhb200_dist_get_layout(ctx, *(ctypes.byref(x) for x in v), None))
+        return tuple(int(x.value) for x in v)
+
+    def global_rowptr(self) -> torch.Tensor:
+        """Device tensor (copy) of this block's GLOBAL row pointers."""
+        lib, ctx = self.engine.lib, self.engine.ctx
+        ptr = ctypes.c_void_p()
+        capi.check(lib, ctx, lib.bhb200_dist_get_global_rowptr_device(ctx, ctypes.byref(ptr)))
+        capi.check(lib, ctx, lib.bhb200_synchronize(ctx))
+        view = _DevicePtr(ptr.value, self.engine.m + 1, "<i8")
+        return torch.as_tensor(view, device=self.device).clone()
+
+
+class _DevicePtr:
+    """A borrowed device pointer as a __cuda_array_interface__ object (read-only use, then clone)."""
+
+    def __init__(self, ptr: int, numel: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (ptr, False), "version": 2}

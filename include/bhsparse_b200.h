@@ -185,6 +185,43 @@ BHB200_API int bhb200_get_stats(const bhb200_ctx *ctx, bhb200_stats *out);
  * reference's dead `_profiling` switch (bhsparse_cuda.h:205-208, 728-733). */
 BHB200_API int bhb200_set_profiling(bhb200_ctx *ctx, int enabled);
 
+/* -- multi-GPU: 1-D row blocks of A, B replicated (the reference is single-GPU,
+ * bhsparse_cuda.h:100-101).  One process per GPU, one context per process; NCCL is called
+ * directly by the library (dlopen of libnccl.so.2 at the first call).
+ *   bhb200_dist_unique_id   any one rank produces the 128-byte NCCL id; the caller hands it to every
+ *                           rank by its own means (MPI, a TCP store, a file).
+ *   bhb200_dist_init        ncclCommInitRank on the context's device; collective.
+ *   bhb200_dist_setup_square  C = B*B: on `root` the three arrays are DEVICE pointers to B (n x n,
+ *                           nnz entries; borrowed), ignored elsewhere.  The root computes the per-row
+ *                           products and the block boundaries on its device (blocks hold equal shares
+ *                           of the intermediate products; a row is never split), then B is
+ *                           broadcast -- boundaries, rowptr, col, and val on a second stream so that it
+ *                           overlaps stage 1 of the first product.  Every rank ends with B replicated
+ *                           and its row block of A set as operands.  Collective.
+ *   bhb200_dist_spgemm      the single-GPU pipeline on the block + ncclAllGather of the int64 nnz(C)
+ *                           of every rank + a device kernel that writes the GLOBAL row pointers of the
+ *                           block (local + offset): no host round trip.  Collective.
+ *   bhb200_dist_get_layout  host view: global rows [row_begin, row_end) of this rank, its first
+ *                           global entry and the total nnz(C) (these two copy nranks int64 from the
+ *                           device), total intermediate products.  Any pointer may be NULL.
+ *   bhb200_dist_get_block_products  intermediate products of every rank's block (nranks int64).
+ *   bhb200_dist_get_global_rowptr_device  device pointer to rows+1 int64 global row pointers.
+ *   bhb200_dist_broadcast_ms  device time of the last set-up (partition + broadcast of B).
+ * C stays row-sharded: rank r's colC / valC (bhb200_get_C_device, bhb200_get_C_range) are the global
+ * entries [nnz_offset, nnz_offset + nnzC_local). */
+#define BHB200_DIST_ID_BYTES 128
+BHB200_API int bhb200_dist_unique_id(void *id);
+BHB200_API int bhb200_dist_init(bhb200_ctx *ctx, int rank, int nranks, const void *id);
+BHB200_API int bhb200_dist_setup_square(bhb200_ctx *ctx, int root, int dtype, int n, int64_t nnz, const int32_t *rowptr,
+                                        const int32_t *col, const void *val);
+BHB200_API int bhb200_dist_spgemm(bhb200_ctx *ctx);
+BHB200_API int bhb200_dist_get_layout(bhb200_ctx *ctx, int64_t *row_begin, int64_t *row_end, int64_t *nnz_offset,
+                                      int64_t *nnz_total, int64_t *products_total);
+BHB200_API int bhb200_dist_get_block_products(bhb200_ctx *ctx, int64_t *block_products);
+BHB200_API int bhb200_dist_get_global_rowptr_device(bhb200_ctx *ctx, const int64_t **rowptr_global);
+BHB200_API int bhb200_dist_broadcast_ms(bhb200_ctx *ctx, float *ms);
+BHB200_API int bhb200_dist_finalize(bhb200_ctx *ctx);
+
 /* bhb200_free_mem replaces bhsparse::free_mem (bhsparse.h:150-177,
  * bhsparse_cuda.h:121-149): releases operands, results and workspace. */
 BHB200_API int bhb200_free_mem(bhb200_ctx *ctx);
