@@ -311,11 +311,18 @@ class Run:
             dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM}[op])
         return t.cpu().tolist()
 
-    def new_engine(self):
-        from benchmark_spgemm_using_csr_b200.dist import CudaEngine, RowBlockSpGEMM
+    def new_engine(self, square=True):
+        """square (C = B*B): partition, NCCL broadcast and offsets run INSIDE the library
+        (bhb200_dist_*, csrc/dist_nccl.cu); otherwise the torch.distributed harness of dist.py."""
+        from benchmark_spgemm_using_csr_b200.dist import CudaEngine, NcclRowBlockSpGEMM, RowBlockSpGEMM
         engine = CudaEngine(self.local_rank)
         engine.use_stream(self.stream.cuda_stream)
-        return engine, RowBlockSpGEMM(engine, self.dev)
+        return engine, (NcclRowBlockSpGEMM(engine, self.dev) if square else RowBlockSpGEMM(engine, self.dev))
+
+    def upload(self, A):
+        """Host CSR -> (rowptr, col, val) tensors on this rank's device (setup, untimed)."""
+        torch = self.torch
+        return tuple(torch.from_numpy(np.ascontiguousarray(x)).to(self.dev) for x in (A.rowptr, A.col, A.val))
 
 
 def timed_steps(run: Run, rb, engine, steps, warmup, sample_clocks):
@@ -333,6 +340,8 @@ def timed_steps(run: Run, rb, engine, steps, warmup, sample_clocks):
     for _ in range(steps):
         nnz_local, off, nnz_total = rb.spgemm()
     ev1.record(run.stream)
+    if nnz_total is None:                   # C-ABI path: offsets and totals stay on the device during the steps
+        _, _, off, nnz_total = rb.layout()
     run.barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3 / steps
     ms_local = ev0.elapsed_time(ev1) / steps
@@ -618,8 +627,11 @@ def main():
     desc = workload_desc(args.workload, world)
     if rank == 0:
         A, B, aeqb = make_workload(args.workload, world, np_dtype)
-    engine, rb = run.new_engine()
-    rb.setup_from_root(A, B, root=0, a_equals_b=aeqb)
+    engine, rb = run.new_engine(square=aeqb)
+    if aeqb:
+        rb.setup_square_from_device_root(run.upload(B) if rank == 0 else None)
+    else:
+        rb.setup_from_root(A, B, root=0, a_equals_b=False)
     meta = rb.meta
     P_total = meta["products"]
     engine.set_profiling(True)
@@ -670,7 +682,9 @@ def main():
             dt = time.perf_counter() - t0
             t_best = dt if t_best is None else min(t_best, dt)
         cpu = {"value": 2.0 * P_total / t_best / 1e9, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-               "sample": f"full workload ({A.rows} rows, {P_total} products), best of 2, {t_best:.3f} s"}
+               "sample": f"full workload ({A.rows} rows, {P_total} products), best of 2, {t_best:.3f} s",
+               # second stated baseline: the reference's own CUDA implementation (oracle/_ref) on this GPU
+               "reference_gpu": reference_gpu_time(A, B, P_total)}
 
     cfg = config_dict(desc, meta["m"], meta["nnzA"], P_total, t["nnz_total"], world)
     cfg["nnzC_rank0"] = t["nnz_local"]

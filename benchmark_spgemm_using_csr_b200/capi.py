@@ -31,7 +31,7 @@ NUM_BIN_NAMES = ["c=0", "p=1", "esc<=32", "g64", "g128", "g256", "g512", "g1024"
 # every symbol include/bhsparse_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = [
     "bhb200_create", "bhb200_destroy", "bhb200_set_stream", "bhb200_last_error", "bhb200_device_name",
-    "bhb200_sm_count", "bhb200_init_data_f64", "bhb200_init_data_f32", "bhb200_init_data_device", "bhb200_operands_aliased",
+    "bhb200_sm_count", "bhb200_init_data_f64", "bhb200_init_data_f32", "bhb200_init_data_device", "bhb200_operands_aliased", "bhb200_get_operands_device",
     "bhb200_warmup", "bhb200_spgemm", "bhb200_synchronize", "bhb200_get_nnzC", "bhb200_get_C_f64",
     "bhb200_get_C_f32", "bhb200_get_rowptrC_i64", "bhb200_get_C_range", "bhb200_get_C_device", "bhb200_copy_C_to_device", "bhb200_get_row_products",
     "bhb200_get_stats", "bhb200_set_profiling", "bhb200_free_mem", "bhb200_version",
@@ -109,6 +109,7 @@ def load(build_if_missing: bool = False):
     L.bhb200_init_data_device.argtypes = [ctxp, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                           c_int, c_void_p, c_void_p, c_void_p]
     L.bhb200_operands_aliased.argtypes = [ctxp]
+    L.bhb200_get_operands_device.argtypes = [ctxp, POINTER(c_int32)] + [POINTER(c_void_p)] * 6
     L.bhb200_warmup.argtypes = [ctxp]
     L.bhb200_spgemm.argtypes = [ctxp]
     L.bhb200_synchronize.argtypes = [ctxp]

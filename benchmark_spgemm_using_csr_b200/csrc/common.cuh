@@ -124,6 +124,7 @@ struct Counters {
     int row_overflow;              // a row's product count did not fit int32
     int bad_B;                     // a row of B is not strictly ascending / has a column outside [0, n)
     int bad_A;                     // a column of A is outside [0, k)
+    int pat_miss;                  // pattern mode: an entry's offset is not in the (cached) offset lists
     int sym_bin[MAX_BINS];
     int num_bin[MAX_BINS];
     int sym_cursor[MAX_BINS];

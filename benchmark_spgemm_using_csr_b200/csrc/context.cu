@@ -283,21 +283,31 @@ void finish_stats(bhb200_ctx *ctx)
 // A and B in ctx->h_sets.  Returns PATTERN_NOT_APPLICABLE if the operands do not qualify (the
 // caller continues with the general path), otherwise the result of the whole product.
 constexpr int PATTERN_NOT_APPLICABLE = 1;
+constexpr int PATTERN_PLAN_STALE = 2;   // speculative run on the cached plan: the operands have other offsets now
 
-int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab)
+// speculative: skip the offset-set detection and reuse the plan of the previous product on this context.
+// k_pat_codes verifies EVERY entry against the plan's offset lists; a miss is reported with the counters,
+// nothing has been written to C by then, and the caller redoes the product with the full detection.
+int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab, bool speculative)
 {
-    const PatSet &sb = ctx->h_sets[1];
-    const PatSet &sa = same_ab ? ctx->h_sets[1] : ctx->h_sets[0];
-    if (sa.overflow || sb.overflow || sa.count > PAT_MAX_OFFS || sb.count > PAT_MAX_OFFS) return PATTERN_NOT_APPLICABLE;
-    const int FILL = PAT_EMPTY;   // what the memset left in unused slots
-    int offA[PAT_MAX_OFFS], offB[PAT_MAX_OFFS], nA = 0, nB = 0;
-    for (int i = 0; i < PAT_SET_SLOTS; ++i) {
-        if (sa.slot[i] != FILL && nA < PAT_MAX_OFFS) offA[nA++] = sa.slot[i];
-        if (sb.slot[i] != FILL && nB < PAT_MAX_OFFS) offB[nB++] = sb.slot[i];
-    }
-    if (nA != sa.count || nB != sb.count) return PATTERN_NOT_APPLICABLE;
     const size_t vs = vsize(ctx->dtype);
-    if (!build_pattern_plan(offA, nA, offB, nB, (int)vs, ctx->plan)) return PATTERN_NOT_APPLICABLE;
+    if (speculative) {
+        if (!ctx->plan.valid || ctx->plan.blob.empty() || ctx->plan.value_size != (int)vs) return PATTERN_NOT_APPLICABLE;
+        if (same_ab && ctx->plan.DA != ctx->plan.DB) return PATTERN_NOT_APPLICABLE;   // (one code array would serve both lists)
+        ctx->plan.reused = true;
+    } else {
+        const PatSet &sb = ctx->h_sets[1];
+        const PatSet &sa = same_ab ? ctx->h_sets[1] : ctx->h_sets[0];
+        if (sa.overflow || sb.overflow || sa.count > PAT_MAX_OFFS || sb.count > PAT_MAX_OFFS) return PATTERN_NOT_APPLICABLE;
+        const int FILL = PAT_EMPTY;   // what the memset left in unused slots
+        int offA[PAT_MAX_OFFS], offB[PAT_MAX_OFFS], nA = 0, nB = 0;
+        for (int i = 0; i < PAT_SET_SLOTS; ++i) {
+            if (sa.slot[i] != FILL && nA < PAT_MAX_OFFS) offA[nA++] = sa.slot[i];
+            if (sb.slot[i] != FILL && nB < PAT_MAX_OFFS) offB[nB++] = sb.slot[i];
+        }
+        if (nA != sa.count || nB != sb.count) return PATTERN_NOT_APPLICABLE;
+        if (!build_pattern_plan(offA, nA, offB, nB, (int)vs, ctx->plan)) return PATTERN_NOT_APPLICABLE;
+    }
     const PatternPlan &plan = ctx->plan;
     cudaStream_t s = ctx->stream;
     bhb200_stats &st = ctx->stats;
@@ -308,6 +318,7 @@ int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab)
         ctx->pat_tb.reserve((size_t)ctx->nnzB + 16, &ctx->dev_bytes) != cudaSuccess ||
         (!same_ab && ctx->pat_ta.reserve((size_t)ctx->nnzA + 16, &ctx->dev_bytes) != cudaSuccess) ||
         ctx->pat_maskB.reserve(((size_t)ctx->k + 1) * 8, &ctx->dev_bytes) != cudaSuccess ||
+        ctx->pat_fullbits.reserve(((size_t)ctx->k / 32 + 2) * 4, &ctx->dev_bytes) != cudaSuccess ||
         ctx->pat_outmask.reserve(((size_t)ctx->m + 1) * plan.nw * 4, &ctx->dev_bytes) != cudaSuccess) {
         cudaGetLastError();
         ctx->plan = PatternPlan();
@@ -322,24 +333,29 @@ int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab)
     Counters *d_ctr = ctx->counters.as<Counters>();
     const long long spanA = (long long)plan.DA.back() - plan.DA.front() + 1, spanB = (long long)plan.DB.back() - plan.DB.front() + 1;
     CU(launch_pat_codes(lc, ctx->k, ctx->n, ctx->B.rowptr, ctx->B.col, t.offsB, t.nDB, spanB, tb, ctx->pat_maskB.as<unsigned long long>(),
-                        &d_ctr->bad_B),
+                        &d_ctr->bad_B, &d_ctr->pat_miss, t.fullB, ctx->pat_fullbits.as<unsigned>()),
        "pattern codes of B");
     if (!same_ab)
-        CU(launch_pat_codes(lc, ctx->m, ctx->k, ctx->A.rowptr, ctx->A.col, t.offsA, t.nDA, spanA, ta, nullptr, &d_ctr->bad_A),
+        CU(launch_pat_codes(lc, ctx->m, ctx->k, ctx->A.rowptr, ctx->A.col, t.offsA, t.nDA, spanA, ta, nullptr, &d_ctr->bad_A,
+                            &d_ctr->pat_miss, 0ull, nullptr),
            "pattern codes of A");
     CU(cudaEventRecord(ctx->ev[1], s), "event");
     // exact nnz(C_i) from the offset masks; also the per-row product counts (compute_nnzCt,
     // bhsparse_cuda.h:210-237) and their total -- the general path's stage-1 kernels are not run
     CU(launch_pat_symbolic(lc, ctx->m, ctx->A, ta, ctx->pat_maskB.as<unsigned long long>(), t, ctx->pat_outmask.as<unsigned>(), rcnt,
-                           ctx->prod.as<int>(), d_ctr, ctx->k, (double)ctx->nnzA / (double)ctx->m),
+                           ctx->prod.as<int>(), d_ctr, ctx->k, (double)ctx->nnzA / (double)ctx->m, ctx->pat_fullbits.as<unsigned>()),
        "pattern symbolic");
     CU(cudaEventRecord(ctx->ev[2], s), "event");
     memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
-    CU(launch_scan(lc, ctx->m, ctx->A.rowptr, ctx->prod.as<int>(), rcnt, ctx->rspan.as<int>(), 0u, nullptr,
+    CU(launch_scan(lc, ctx->m, ctx->A.rowptr, ctx->prod.as<int>(), rcnt, nullptr, 0u, nullptr,
                    ctx->rowoff64.as<int64_t>(), ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
        "row pointer scan");
     CU(cudaMemcpyAsync(ctx->h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s), "D2H counters");
     CU(cudaStreamSynchronize(s), "pattern symbolic / scan");
+    if (ctx->h_ctr->pat_miss) {
+        ctx->plan = PatternPlan();   // (speculative or not: these lists do not describe the operands)
+        return speculative ? PATTERN_PLAN_STALE : fail(ctx, BHB200_ERR_CUDA, "pattern mode: offset lists inconsistent with the operands");
+    }
     if (ctx->h_ctr->bad_B) return fail(ctx, BHB200_ERR_INVALID, "rows of B must be sorted by column, duplicate-free and inside [0, n)");
     if (ctx->h_ctr->bad_A) return fail(ctx, BHB200_ERR_INVALID, "a column index of A is outside [0, k)");
     ctx->nnzC = (int64_t)ctx->h_ctr->nnzC;
@@ -423,7 +439,10 @@ int bhb200_create(bhb200_ctx **out, int device)
         delete ctx;
         return BHB200_ERR_CUDA;
     }
-    if (const char *pm = getenv("BHB200_PATTERN")) ctx->pattern_enable = strcmp(pm, "off") != 0;
+    if (const char *pm = getenv("BHB200_PATTERN")) {
+        ctx->pattern_enable = strcmp(pm, "off") != 0;
+        ctx->pattern_speculate = strcmp(pm, "detect") != 0;   // "detect": run the offset-set pass on every call
+    }
     if (const char *dc = getenv("BHB200_DEBUG_DEVICE_CAP")) ctx->device_cap = (size_t)atoll(dc);
     if (const char *dm = getenv("BHB200_DIRECT")) {
         ctx->direct_mode = strcmp(dm, "off") != 0;
@@ -453,7 +472,7 @@ int bhb200_free_mem(bhb200_ctx *ctx)
     release_operands(ctx);
     ctx->plan = PatternPlan();
     ctx->last_pattern = false;
-    DevBuf *bufs[] = {&ctx->pat_sets, &ctx->pat_ta, &ctx->pat_tb, &ctx->pat_maskB, &ctx->pat_outmask, &ctx->pat_tables,
+    DevBuf *bufs[] = {&ctx->pat_sets, &ctx->pat_ta, &ctx->pat_tb, &ctx->pat_maskB, &ctx->pat_outmask, &ctx->pat_tables, &ctx->pat_fullbits,
                       &ctx->ct_off, &ctx->ct_col, &ctx->ct_val, &ctx->retry_q,
                       &ctx->brange, &ctx->rlo, &ctx->rspan, &ctx->wl_off, &ctx->wl_cnt, &ctx->wl_idx, &ctx->wl_bits,
                       &ctx->prod, &ctx->rc, &ctx->queue, &ctx->rowoff64, &ctx->rowptr32, &ctx->blocksums,
@@ -597,6 +616,18 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         cudaGetLastError();
         try_pattern = false;
     }
+    if (try_pattern && ctx->plan.valid && ctx->pattern_speculate) {
+        // the previous product on this context ran in pattern mode: reuse its plan without the detection
+        // pass; every entry is verified against it (k_pat_codes), a miss brings us back here
+        if (ctx->wait_before_values) {
+            CU(cudaStreamWaitEvent(s, ctx->wait_before_values, 0), "wait for the broadcast of B's values");
+            ctx->wait_before_values = nullptr;
+        }
+        rc = run_pattern(ctx, lc, same_ab, true);
+        if (rc != PATTERN_NOT_APPLICABLE && rc != PATTERN_PLAN_STALE) return rc;
+        CU(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s), "zero counters");
+        st.pattern_mode = 0;
+    }
     if (try_pattern) {
         PatSet *sets = ctx->pat_sets.as<PatSet>();
         CU(cudaMemsetAsync(sets, 0x80, 2 * sizeof(PatSet), s), "init offset sets");   // slots = PAT_EMPTY
@@ -611,8 +642,10 @@ int bhb200_spgemm(bhb200_ctx *ctx)
             CU(cudaStreamWaitEvent(s, ctx->wait_before_values, 0), "wait for the broadcast of B's values");
             ctx->wait_before_values = nullptr;
         }
-        rc = run_pattern(ctx, lc, same_ab);
+        rc = run_pattern(ctx, lc, same_ab, false);
         if (rc != PATTERN_NOT_APPLICABLE) return rc;
+        ctx->plan = PatternPlan();   // these operands are not diagonal-structured: no speculation next time
+        CU(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s), "zero counters");
     }
     int *rlo = ctx->rlo.as<int>();
     int *rspan = ctx->rspan.as<int>();
@@ -969,6 +1002,27 @@ int bhb200_synchronize(bhb200_ctx *ctx)
     if (!ctx) return BHB200_ERR_INVALID;
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     CU(cudaStreamSynchronize(ctx->stream), "synchronize");
+    return BHB200_SUCCESS;
+}
+
+int bhb200_get_operands_device(const bhb200_ctx *ctx, int32_t *dims, const int32_t **rowptrA, const int32_t **colA,
+                               const void **valA, const int32_t **rowptrB, const int32_t **colB, const void **valB)
+{
+    if (!ctx || !ctx->have_data) return BHB200_ERR_INVALID;
+    if (dims) {
+        dims[0] = ctx->m;
+        dims[1] = ctx->k;
+        dims[2] = ctx->n;
+        dims[3] = ctx->nnzA;
+        dims[4] = ctx->nnzB;
+        dims[5] = ctx->dtype;
+    }
+    if (rowptrA) *rowptrA = ctx->A.rowptr;
+    if (colA) *colA = ctx->A.col;
+    if (valA) *valA = ctx->A.val;
+    if (rowptrB) *rowptrB = ctx->B.rowptr;
+    if (colB) *colB = ctx->B.col;
+    if (valB) *valB = ctx->B.val;
     return BHB200_SUCCESS;
 }
 

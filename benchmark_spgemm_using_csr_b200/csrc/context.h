@@ -99,11 +99,12 @@ struct bhb200_ctx {
     bhb::DevBuf brange, rlo, rspan, wl_off, wl_cnt, wl_idx, wl_bits;   // span info + word-list pool (range kernels)
     bhb::DevBuf ct_off, ct_col, ct_val, retry_q;                       // direct mode: staging buffer (Ct) + retry queues
     // diagonal-pattern mode (stage_pattern.cuh): offset sets, per-entry codes, masks, tables
-    bhb::DevBuf pat_sets, pat_ta, pat_tb, pat_maskB, pat_outmask, pat_tables;
+    bhb::DevBuf pat_sets, pat_ta, pat_tb, pat_maskB, pat_outmask, pat_tables, pat_fullbits;
     bhb::PatSet *h_sets = nullptr;    // pinned, [2]
     bhb::PatternPlan plan;
     size_t device_cap = ~(size_t)0;   // BHB200_DEBUG_DEVICE_CAP: largest single buffer the device may hold (tests)
     int pattern_enable = 1;      // BHB200_PATTERN=off disables
+    int pattern_speculate = 1;   // reuse the previous plan without the detection pass (verified; BHB200_PATTERN=detect disables)
     bool last_pattern = false;   // the last product ran in pattern mode
     bhb::PatTables last_tables{};
     const unsigned char *last_ta = nullptr, *last_tb = nullptr;

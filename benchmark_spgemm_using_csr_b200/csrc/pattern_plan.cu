@@ -13,7 +13,7 @@ namespace bhb {
 // the outputs with `nb` residues (nb = 32 for 4-byte, 16 for 8-byte values) against those groups,
 // then position = residue + nb * (index inside the residue class).  Conflicts that remain only
 // cost replays; correctness does not depend on the layout.
-static void choose_layout(int nDA, int nDB, int nD, const std::vector<unsigned char> &mlog, int nb,
+static void choose_layout(int nDA, int nDB, int nD, const std::vector<unsigned char> &mlog, int nb, const long long *offs,
                           std::vector<unsigned char> &pos, int &acc_len)
 {
     const int cap = 256 / nb;                       // positions stay below 256
@@ -59,6 +59,85 @@ static void choose_layout(int nDA, int nDB, int nD, const std::vector<unsigned c
             moved |= take != cur;
         }
         if (!moved) break;
+    }
+    // Second candidate family for lattice-shaped offset sets (stencils on structured grids: the offsets are
+    // z*S2 + y*S1 + x).  Coordinates are recovered from the sorted offsets by peeling runs of the smallest
+    // gap, level by level; then every linear colouring (x + b*y + a*z) mod nb is scored with the true
+    // cost -- the sum over lane groups of the largest bank multiplicity = shared-memory wavefronts -- and
+    // the best assignment (greedy included) wins.  The 27-point stencil in doubles: greedy 77, best linear
+    // 54 = conflict-free (profiles/r02_notes.md).
+    auto true_cost = [&](const std::vector<int> &r) {
+        int total = 0;
+        std::vector<int> cnt(nb);
+        for (const auto &st : sets) {
+            std::fill(cnt.begin(), cnt.end(), 0);
+            int mx = 0;
+            for (int o : st) mx = std::max(mx, ++cnt[r[o]]);
+            total += mx;
+        }
+        return total;
+    };
+    if (!sets.empty() && offs && nD >= 4) {
+        // coord[level][o]: position of o inside its run at that level
+        std::vector<std::vector<int>> coord;
+        std::vector<long long> cur(offs, offs + nD);      // sorted representatives of the current level
+        std::vector<int> owner(nD);                        // element o -> index in `cur`
+        for (int o = 0; o < nD; ++o) owner[o] = o;
+        for (int level = 0; level < 4 && cur.size() > 1; ++level) {
+            long long g = cur[1] - cur[0];
+            for (size_t i = 2; i < cur.size(); ++i) g = std::min(g, cur[i] - cur[i - 1]);
+            std::vector<int> run_of(cur.size()), pos_in(cur.size());
+            std::vector<long long> starts;
+            for (size_t i = 0; i < cur.size(); ++i) {
+                if (i == 0 || cur[i] - cur[i - 1] != g) starts.push_back(cur[i]);
+                run_of[i] = (int)starts.size() - 1;
+                pos_in[i] = (i == 0 || cur[i] - cur[i - 1] != g) ? 0 : pos_in[i - 1] + 1;
+            }
+            std::vector<int> c(nD);
+            for (int o = 0; o < nD; ++o) {
+                c[o] = pos_in[owner[o]];
+                owner[o] = run_of[owner[o]];
+            }
+            coord.push_back(std::move(c));
+            if (starts.size() == cur.size()) break;        // no runs at this level: not a lattice
+            cur.swap(starts);
+        }
+        if (cur.size() > 1 && coord.size() < 4) {          // whatever is left: its index is the last coordinate
+            std::vector<int> c(nD);
+            for (int o = 0; o < nD; ++o) c[o] = owner[o];
+            coord.push_back(std::move(c));
+        }
+        const int nl = (int)coord.size();
+        if (nl >= 2 && nl <= 4) {
+            int best_cost = true_cost(res);
+            std::vector<int> cand(nD), coef(nl, 0);
+            long long combos = 1;
+            for (int l = 1; l < nl; ++l) combos *= nb;
+            if (combos <= 4096) {
+                for (long long id = 0; id < combos && best_cost > (int)sets.size(); ++id) {
+                    long long t = id;
+                    coef[0] = 1;
+                    for (int l = 1; l < nl; ++l) {
+                        coef[l] = (int)(t % nb);
+                        t /= nb;
+                    }
+                    std::vector<int> fill(nb, 0);
+                    bool ok = true;
+                    for (int o = 0; o < nD && ok; ++o) {
+                        int v = 0;
+                        for (int l = 0; l < nl; ++l) v += coef[l] * coord[l][o];
+                        cand[o] = v % nb;
+                        ok = ++fill[cand[o]] <= cap;
+                    }
+                    if (!ok) continue;
+                    const int c = true_cost(cand);
+                    if (c < best_cost) {
+                        best_cost = c;
+                        res = cand;
+                    }
+                }
+            }
+        }
     }
     std::vector<int> next(nb, 0);
     pos.assign(nD, 0);
@@ -108,7 +187,7 @@ bool build_pattern_plan(const int *offsA, int nA, const int *offsB, int nB, int 
             mlog[(size_t)ja * nB + jb] = (unsigned char)o;
             pfull[(size_t)ja * nw + (o >> 5)] |= 1u << (o & 31);
         }
-    choose_layout(nA, nB, nD, mlog, value_size == 8 ? 16 : 32, pos, plan.acc_len);
+    choose_layout(nA, nB, nD, mlog, value_size == 8 ? 16 : 32, sums.data(), pos, plan.acc_len);
     for (size_t i = 0; i < mlog.size(); ++i) mphys[i] = pos[mlog[i]];
     // blob: byte tables first, then the 4-byte tables (aligned)
     const size_t nM = (size_t)nA * nB;

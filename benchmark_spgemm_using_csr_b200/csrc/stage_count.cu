@@ -298,10 +298,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int m, const
         const long long i = base + (long long)it * SCAN_THREADS + threadIdx.x;
         int b = -1;
         unsigned long long wp = 0ull, wc = 0ull, wa = 0ull;
-        if (i < m) {
+        if (i < m) s += rc[i];
+        if (i < m && rspan) {   // (rspan == nullptr: row pointers only, no numeric bins -- pattern mode)
             const int c = rc[i];
             const int p = prod[i];
-            s += c;
             const int span = rspan[i];
             const int sb = sym_bin_of(p, span);
             b = (((spec_mask >> sb) & 1u) && ct_off[i] >= 0) ? (int)NB_COPY : num_bin_of(p, c, span);

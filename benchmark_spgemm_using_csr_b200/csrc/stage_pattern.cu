@@ -4,7 +4,7 @@
 #include <cstdlib>
 
 #ifndef PAT_DEFAULT_MINB
-#define PAT_DEFAULT_MINB 8
+#define PAT_DEFAULT_MINB 6
 #endif
 
 namespace bhb {
@@ -118,16 +118,20 @@ constexpr int PAT_DIRECT_SPAN = 40 * 1024;
 template <bool DIRECT>
 __global__ void __launch_bounds__(256) k_pat_codes(const int rows, const int ncols, const int *__restrict__ rowptr,
                                                    const int *__restrict__ col, const int *__restrict__ offs,
-                                                   const int noffs, unsigned char *__restrict__ code,
-                                                   unsigned long long *__restrict__ rowmask, int *__restrict__ bad)
+                                                   const int noffs, const int span, unsigned char *__restrict__ code,
+                                                   unsigned long long *__restrict__ rowmask, int *__restrict__ bad,
+                                                   int *__restrict__ miss)
 {
     __shared__ int s_offs[PAT_MAX_OFFS];
     extern __shared__ unsigned char s_tab[];
     if (threadIdx.x < PAT_MAX_OFFS) s_offs[threadIdx.x] = threadIdx.x < noffs ? offs[threadIdx.x] : 0x7fffffff;
+    if constexpr (DIRECT) {
+        for (int i = threadIdx.x * 16; i < span; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(s_tab + i) = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
     __syncthreads();
     const int dmin = s_offs[0];
     if constexpr (DIRECT) {
-        if (threadIdx.x < noffs) s_tab[s_offs[threadIdx.x] - dmin] = (unsigned char)threadIdx.x;   // (other bytes are never read)
+        if (threadIdx.x < noffs) s_tab[s_offs[threadIdx.x] - dmin] = (unsigned char)threadIdx.x;
         __syncthreads();
     }
     const int gl = threadIdx.x & 7;
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(256) k_pat_codes(const int rows, const int nco
     for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < rows; r += stride) {
         const int s = rowptr[r], e = rowptr[r + 1];
         unsigned long long mask = 0ull;
-        bool wrong = e < s;
+        bool wrong = e < s, unknown = false;
         for (int p = s + gl; p < e; p += 8) {
             const int c = col[p];
             // the operand preconditions (see k_b_row_ranges): columns inside the matrix; for B
@@ -143,18 +147,27 @@ __global__ void __launch_bounds__(256) k_pat_codes(const int rows, const int nco
             wrong |= (unsigned)c >= (unsigned)ncols;
             if (rowmask) wrong |= (p > s && col[p - 1] >= c);
             const int d = c - (int)r;
-            int lo = 0;   // index of d in the sorted list (d is in it: the list is the exact set)
+            int lo = 0;   // index of d in the sorted offset list
             if constexpr (DIRECT) {
-                lo = s_tab[d - dmin];
+                const unsigned rel = (unsigned)(d - dmin);
+                lo = rel < (unsigned)span ? s_tab[rel] : 0xff;
             } else {
 #pragma unroll
                 for (int step = PAT_MAX_OFFS / 2; step > 0; step >>= 1)
                     if (s_offs[lo + step - 1] < d) lo += step;
+                if (s_offs[lo] != d) lo = 0xff;
+            }
+            // an offset that is not in the list: the (cached) plan does not describe this matrix any
+            // more -- flagged, the caller re-runs the detection; a valid code keeps the later kernels in bounds
+            if (lo >= noffs) {
+                unknown = true;
+                lo = 0;
             }
             code[p] = (unsigned char)lo;
             mask |= 1ull << lo;
         }
         if (wrong) *bad = 1;
+        if (unknown) *miss = 1;
         if (rowmask) {
             mask |= __shfl_xor_sync(group_mask<8>(threadIdx.x & 31), mask, 1, 8);
             mask |= __shfl_xor_sync(group_mask<8>(threadIdx.x & 31), mask, 2, 8);
@@ -164,8 +177,20 @@ __global__ void __launch_bounds__(256) k_pat_codes(const int rows, const int nco
     }
 }
 
+// one bit per row of B: the row holds every offset of DB (then its image under any A offset is the
+// precomputed P[ja] and k_pat_symbolic does not need the 8-byte mask)
+__global__ void __launch_bounds__(256) k_pat_fullbits(const int rows, const unsigned long long *__restrict__ rowmask,
+                                                      const unsigned long long full, unsigned *__restrict__ bits)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool f = r < rows && rowmask[r] == full;
+    const unsigned b = __ballot_sync(FULL, f);
+    if ((threadIdx.x & 31) == 0 && (r >> 5) <= ((long long)rows - 1) >> 5) bits[r >> 5] = b;
+}
+
 cudaError_t launch_pat_codes(const LaunchCtx &lc, int rows, int ncols, const int *rowptr, const int *col, const int *offs,
-                             int noffs, long long span, unsigned char *code, unsigned long long *rowmask, int *bad)
+                             int noffs, long long span, unsigned char *code, unsigned long long *rowmask, int *bad, int *miss,
+                             unsigned long long full, unsigned *fullbits)
 {
     if (rows <= 0) return cudaSuccess;
     long long blocks = ((long long)rows * 8 + 255) / 256;
@@ -174,9 +199,13 @@ cudaError_t launch_pat_codes(const LaunchCtx &lc, int rows, int ncols, const int
     ++*lc.launches;
     if (span > 0 && span <= PAT_DIRECT_SPAN) {
         const size_t smem = ((size_t)span + 15) & ~(size_t)15;
-        k_pat_codes<true><<<(int)blocks, 256, smem, lc.stream>>>(rows, ncols, rowptr, col, offs, noffs, code, rowmask, bad);
+        k_pat_codes<true><<<(int)blocks, 256, smem, lc.stream>>>(rows, ncols, rowptr, col, offs, noffs, (int)span, code, rowmask, bad, miss);
     } else {
-        k_pat_codes<false><<<(int)blocks, 256, 0, lc.stream>>>(rows, ncols, rowptr, col, offs, noffs, code, rowmask, bad);
+        k_pat_codes<false><<<(int)blocks, 256, 0, lc.stream>>>(rows, ncols, rowptr, col, offs, noffs, 0, code, rowmask, bad, miss);
+    }
+    if (rowmask && fullbits) {
+        ++*lc.launches;
+        k_pat_fullbits<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, rowmask, full, fullbits);
     }
     return cudaGetLastError();
 }
@@ -193,16 +222,19 @@ __global__ void __launch_bounds__(256) k_pat_symbolic(const int m, const int *__
                                                       const unsigned char *__restrict__ ta,
                                                       const unsigned long long *__restrict__ maskB, const PatTables t,
                                                       unsigned *__restrict__ outmask, int *__restrict__ rc,
-                                                      int *__restrict__ prod, Counters *__restrict__ ctr, const int k)
+                                                      int *__restrict__ prod, Counters *__restrict__ ctr, const int k,
+                                                      const unsigned *__restrict__ fullbits)
 {
     __shared__ unsigned long long s_total;
     __shared__ int s_max;
     __shared__ unsigned s_pfull[PAT_MAX_OFFS * NW];
+    __shared__ unsigned char s_mlog[PAT_MAX_OFFS * PAT_MAX_OFFS];
     if (threadIdx.x == 0) {
         s_total = 0ull;
         s_max = 0;
     }
     for (int i = threadIdx.x; i < t.nDA * NW; i += blockDim.x) s_pfull[i] = t.pfull[i];
+    for (int i = threadIdx.x; i < t.nDA * t.nDB; i += blockDim.x) s_mlog[i] = t.mlog[i];
     __syncthreads();
     const int gl = threadIdx.x & 7;
     const unsigned gmask = group_mask<8>(threadIdx.x & 31);
@@ -228,7 +260,11 @@ __global__ void __launch_bounds__(256) k_pat_symbolic(const int m, const int *__
                 ck[u] = in ? colA[j] : -1;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) mb[u] = ((unsigned)ck[u] < (unsigned)k) ? maskB[ck[u]] : 0ull;   // (bad columns are flagged by k_pat_codes)
+            for (int u = 0; u < 4; ++u) {   // (bad columns are flagged by k_pat_codes)
+                const bool okc = (unsigned)ck[u] < (unsigned)k;
+                const bool isfull = okc && ((__ldg(fullbits + (ck[u] >> 5)) >> (ck[u] & 31)) & 1u);
+                mb[u] = isfull ? t.fullB : (okc ? maskB[ck[u]] : 0ull);   // the 8-byte mask only for partial rows
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 unsigned long long m1 = mb[u];
@@ -236,14 +272,26 @@ __global__ void __launch_bounds__(256) k_pat_symbolic(const int m, const int *__
                 if (m1 == t.fullB) {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) mk[w] |= s_pfull[ja[u] * NW + w];
-                } else {
-                    while (m1) {
-                        const int jb = __ffsll((long long)m1) - 1;
-                        m1 &= m1 - 1;
-                        const int o = t.mlog[ja[u] * t.nDB + jb];
+                } else if (m1) {
+                    // partial B row (boundary cells of a grid): the image of its offset set.  Walk whichever is
+                    // shorter, the offsets present (set their output bits) or the ones missing (clear them
+                    // from the full-row image; for a fixed A offset jb -> output is injective).
+                    const unsigned long long miss = t.fullB & ~m1;
+                    const bool by_missing = __popcll(miss) < __popcll(m1);
+                    unsigned long long walk = by_missing ? miss : m1;
+                    unsigned img[NW];
 #pragma unroll
-                        for (int w = 0; w < NW; ++w) mk[w] |= ((o >> 5) == w) ? (1u << (o & 31)) : 0u;
+                    for (int w = 0; w < NW; ++w) img[w] = by_missing ? s_pfull[ja[u] * NW + w] : 0u;
+                    const unsigned char *mrow = s_mlog + ja[u] * t.nDB;
+                    while (walk) {
+                        const int jb = __ffsll((long long)walk) - 1;
+                        walk &= walk - 1;
+                        const int o = mrow[jb];
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) img[w] ^= ((o >> 5) == w) ? (1u << (o & 31)) : 0u;   // set, or clear from the full image
                     }
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) mk[w] |= img[w];
                 }
             }
         }
@@ -289,8 +337,10 @@ __global__ void __launch_bounds__(256) k_pat_symbolic_warp(const int m, const in
                                                            const unsigned char *__restrict__ ta,
                                                            const unsigned long long *__restrict__ maskB, const PatTables t,
                                                            unsigned *__restrict__ outmask, int *__restrict__ rc,
-                                                           int *__restrict__ prod, Counters *__restrict__ ctr, const int k)
+                                                           int *__restrict__ prod, Counters *__restrict__ ctr, const int k,
+                                                           const unsigned *__restrict__ fullbits)
 {
+    (void)fullbits;
     __shared__ unsigned long long s_total;
     __shared__ int s_max;
     __shared__ unsigned s_pfull[PAT_MAX_OFFS * NW];
@@ -356,7 +406,8 @@ __global__ void __launch_bounds__(256) k_pat_symbolic_warp(const int m, const in
 }
 
 cudaError_t launch_pat_symbolic(const LaunchCtx &lc, int m, Csr A, const unsigned char *ta, const unsigned long long *maskB,
-                                PatTables t, unsigned *outmask, int *rc, int *prod, Counters *ctr, int k, double avg_row)
+                                PatTables t, unsigned *outmask, int *rc, int *prod, Counters *ctr, int k, double avg_row,
+                                const unsigned *fullbits)
 {
     if (m <= 0) return cudaSuccess;
     ++*lc.launches;
@@ -365,10 +416,10 @@ cudaError_t launch_pat_symbolic(const LaunchCtx &lc, int m, Csr A, const unsigne
         long long blocks = ((long long)m + 7) / 8;
         if (blocks > cap) blocks = cap;
         switch (t.nw) {
-        case 1: k_pat_symbolic_warp<1><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k); break;
-        case 2: k_pat_symbolic_warp<2><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k); break;
-        case 4: k_pat_symbolic_warp<4><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k); break;
-        case 8: k_pat_symbolic_warp<8><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k); break;
+        case 1: k_pat_symbolic_warp<1><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k, fullbits); break;
+        case 2: k_pat_symbolic_warp<2><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k, fullbits); break;
+        case 4: k_pat_symbolic_warp<4><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k, fullbits); break;
+        case 8: k_pat_symbolic_warp<8><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k, fullbits); break;
         default: return cudaErrorInvalidValue;
         }
         return cudaGetLastError();
@@ -376,10 +427,10 @@ cudaError_t launch_pat_symbolic(const LaunchCtx &lc, int m, Csr A, const unsigne
     long long blocks = ((long long)m * 8 + 255) / 256;
     if (blocks > cap * 2) blocks = cap * 2;
     switch (t.nw) {
-    case 1: k_pat_symbolic<1><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k); break;
-    case 2: k_pat_symbolic<2><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k); break;
-    case 4: k_pat_symbolic<4><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k); break;
-    case 8: k_pat_symbolic<8><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k); break;
+    case 1: k_pat_symbolic<1><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k, fullbits); break;
+    case 2: k_pat_symbolic<2><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k, fullbits); break;
+    case 4: k_pat_symbolic<4><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k, fullbits); break;
+    case 8: k_pat_symbolic<8><<<(int)blocks, 256, 0, lc.stream>>>(m, A.rowptr, A.col, ta, maskB, t, outmask, rc, prod, ctr, k, fullbits); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -426,6 +477,70 @@ __device__ __forceinline__ float lds_val(unsigned a, float)
 __device__ __forceinline__ void sts_val(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ void sts_val(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
+// Predicated (not branched) element load and accumulate of the hot loop: inactive lanes issue no memory
+// access at all, and the warp stays converged.
+__device__ __forceinline__ void pat_load_if(const bool on, const unsigned char *cp, const double *vp, int &jb, double &bv)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.s32 p, %2, 0;\n"
+        "@p ld.global.nc.u8 %0, [%3];\n"
+        "@p ld.global.nc.f64 %1, [%4];\n"
+        "}\n"
+        : "+r"(jb), "+d"(bv)
+        : "r"((int)on), "l"(cp), "l"(vp)
+        : "memory");
+}
+__device__ __forceinline__ void pat_load_if(const bool on, const unsigned char *cp, const float *vp, int &jb, float &bv)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.s32 p, %2, 0;\n"
+        "@p ld.global.nc.u8 %0, [%3];\n"
+        "@p ld.global.nc.f32 %1, [%4];\n"
+        "}\n"
+        : "+r"(jb), "+f"(bv)
+        : "r"((int)on), "l"(cp), "l"(vp)
+        : "memory");
+}
+// acc[ mphys[mp] ] += av * bv   (mp, acc_s: shared-space addresses)
+__device__ __forceinline__ void pat_accum_if(const bool on, const unsigned mp, const unsigned acc_s, const double av, const double bv)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 q, a;\n"
+        ".reg .f64 v;\n"
+        "setp.ne.s32 p, %0, 0;\n"
+        "@p ld.shared.u8 q, [%1];\n"
+        "@p mad.lo.u32 a, q, 8, %2;\n"
+        "@p ld.shared.f64 v, [a];\n"
+        "@p fma.rn.f64 v, %3, %4, v;\n"
+        "@p st.shared.f64 [a], v;\n"
+        "}\n" ::"r"((int)on),
+        "r"(mp), "r"(acc_s), "d"(av), "d"(bv)
+        : "memory");
+}
+__device__ __forceinline__ void pat_accum_if(const bool on, const unsigned mp, const unsigned acc_s, const float av, const float bv)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 q, a;\n"
+        ".reg .f32 v;\n"
+        "setp.ne.s32 p, %0, 0;\n"
+        "@p ld.shared.u8 q, [%1];\n"
+        "@p mad.lo.u32 a, q, 4, %2;\n"
+        "@p ld.shared.f32 v, [a];\n"
+        "@p fma.rn.f32 v, %3, %4, v;\n"
+        "@p st.shared.f32 [a], v;\n"
+        "}\n" ::"r"((int)on),
+        "r"(mp), "r"(acc_s), "f"(av), "f"(bv)
+        : "memory");
+}
+
 template <typename VT>
 struct PatRec;
 template <>
@@ -471,15 +586,14 @@ k_pat_numeric(const int m, const int *__restrict__ rowptrA, const int *__restric
     const int gshift = lane & ~(G - 1);
     const unsigned gbits = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
     const int acc_len = t.acc_len;
-    const size_t per_group = (size_t)(acc_len + G) * sizeof(VT) + (size_t)G * 16;   // accumulators + sink slots | records
+    const size_t per_group = (size_t)acc_len * sizeof(VT) + (size_t)G * 16;   // accumulators | records
     unsigned char *mine = smem_raw + tab_bytes + (size_t)gib * per_group;
     VT *acc = reinterpret_cast<VT *>(mine);
-    int4 *rec = reinterpret_cast<int4 *>(mine + (size_t)(acc_len + G) * sizeof(VT));
+    int4 *rec = reinterpret_cast<int4 *>(mine + (size_t)acc_len * sizeof(VT));
     const int nDB = t.nDB, nD = t.nD, nw = t.nw;
     (void)gshift;
     (void)gbits;
     const unsigned acc_s = sm_addr(acc), rec_s = sm_addr(rec), mphys_s = sm_addr(s_mphys);
-    const int sink = acc_len + gl;   // private slot for lanes beyond the end of a B row
 
     for (long long q0 = (long long)blockIdx.x * groups_per_block + (gib & ~(GPW - 1)); q0 < m;
          q0 += (long long)gridDim.x * groups_per_block) {
@@ -503,9 +617,9 @@ k_pat_numeric(const int m, const int *__restrict__ rowptrA, const int *__restric
             __syncwarp();
             const int cnt = min(G, max_na - base);   // warp-uniform
             // Software pipeline, two register sets in ping-pong: the loads of B row tt+1 (one code byte, one
-            // value per lane) are issued before B row tt is accumulated.  Branch-free: a lane beyond the
-            // end of its B row loads element 0 of the arrays and accumulates into its private sink slot
-            // (acc[acc_len + gl]), so the warp never diverges and every step is straight-line code.
+            // value per lane) are issued before B row tt is accumulated.  Branch-free: lanes beyond the end of
+            // their B row are predicated off (no memory access), the warp never diverges and every step is
+            // straight-line code.
             int4 rA, rB;
             int jbA = 0, jbB = 0;
             VT bvA = VT(0), bvB = VT(0);
@@ -514,15 +628,14 @@ k_pat_numeric(const int m, const int *__restrict__ rowptrA, const int *__restric
     do {                                                                  \
         R = lds_v4(rec_s + (unsigned)(TT) * 16u);                        \
         ON = gl < (R.y & 0xffff);                                         \
-        const int idx__ = ON ? R.x + gl : 0;                              \
+        /* lanes past the end re-read the row's first element (same cache line, no branch); empty row: element 0 */ \
+        const int idx__ = ON ? R.x + gl : ((R.y & 0xffff) ? R.x : 0);    \
         JB = tb[idx__];                                                   \
         BV = valB[idx__];                                                 \
     } while (0)
 #define PAT_ACCUM(R, JB, BV, ON)                                                          \
     do {                                                                                   \
-        const int p__ = ON ? lds_u8(mphys_s + (unsigned)(R.y >> 16) + (unsigned)(JB)) : sink; \
-        const unsigned a__ = acc_s + (unsigned)p__ * (unsigned)sizeof(VT);                 \
-        sts_val(a__, fma(PatRec<VT>::val(R), BV, lds_val(a__, VT(0))));                    \
+        pat_accum_if(ON, mphys_s + (unsigned)(R.y >> 16) + (unsigned)(JB), acc_s, PatRec<VT>::val(R), BV); \
         if constexpr (LONGB) {                                                             \
             const int len__ = R.y & 0xffff;                                                \
             _Pragma("unroll 1") for (int off = G + gl; off < len__; off += G) {            \
@@ -573,7 +686,7 @@ static cudaError_t launch_pat_numeric_tbl(const LaunchCtx &lc, int m, Csr A, Csr
     const int threads = 256;
     const int groups = threads / G;
     const size_t tab_bytes = ((size_t)t.nD * 4 + (size_t)t.nDA * t.nDB + (size_t)t.nD + 15) & ~(size_t)15;
-    const size_t smem = tab_bytes + (size_t)groups * ((size_t)(t.acc_len + G) * sizeof(VT) + (size_t)G * 16);
+    const size_t smem = tab_bytes + (size_t)groups * ((size_t)t.acc_len * sizeof(VT) + (size_t)G * 16);
     auto kern = k_pat_numeric<VT, G, MINB, LONGB>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

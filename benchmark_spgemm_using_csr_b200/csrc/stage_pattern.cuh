@@ -52,10 +52,14 @@ struct PatTables {
 cudaError_t launch_offset_set(const LaunchCtx &lc, int rows, const int *rowptr, const int *col, PatSet *set);
 // bad: set to 1 if a column is outside [0, ncols) or (rowmask != nullptr) a row is not strictly ascending
 // span = largest - smallest offset + 1 (a small span selects the direct-table kernel)
+// miss: set to 1 if an entry's offset is not in `offs` (a cached plan no longer describes the matrix)
+// fullbits (with rowmask): one bit per row, "holds every offset" (rowmask == full)
 cudaError_t launch_pat_codes(const LaunchCtx &lc, int rows, int ncols, const int *rowptr, const int *col, const int *offs,
-                             int noffs, long long span, unsigned char *code, unsigned long long *rowmask, int *bad);
+                             int noffs, long long span, unsigned char *code, unsigned long long *rowmask, int *bad, int *miss,
+                             unsigned long long full, unsigned *fullbits);
 cudaError_t launch_pat_symbolic(const LaunchCtx &lc, int m, Csr A, const unsigned char *ta, const unsigned long long *maskB,
-                                PatTables t, unsigned *outmask, int *rc, int *prod, Counters *ctr, int k, double avg_row);
+                                PatTables t, unsigned *outmask, int *rc, int *prod, Counters *ctr, int k, double avg_row,
+                                const unsigned *fullbits);
 cudaError_t launch_pat_numeric(const LaunchCtx &lc, int dtype, int m, Csr A, Csr B, const unsigned char *ta,
                                const unsigned char *tb, PatTables t, const unsigned *outmask, const int64_t *rowoff,
                                int *colC, void *valC);

@@ -378,17 +378,17 @@ class NcclRowBlockSpGEMM:
             uid = ctypes.create_string_buffer(box[0], capi.DIST_ID_BYTES)
         capi.check(lib, ctx, lib.bhb200_dist_init(ctx, self.rank, self.world, uid))
 
-    def setup_square_from_device_root(self, B_dev, n: int, root: int = 0):
+    def setup_square_from_device_root(self, B_dev, n: int = 0, root: int = 0):
         lib, ctx = self.engine.lib, self.engine.ctx
         self.engine._order_after_producers()
         info = [None]
         if self.rank == root:
             Brp, Bc, Bv = B_dev
             self._keep = B_dev
-            info = [(int(Bc.numel()), str(Bv.dtype).replace("torch.", ""))]
+            info = [(int(Bc.numel()), str(Bv.dtype).replace("torch.", ""), int(Brp.numel()) - 1)]
         if self.world > 1:
             dist.broadcast_object_list(info, src=root, group=self.group)
-        nnz, dname = info[0]
+        nnz, dname, n = info[0]              # (n is taken from the root's arrays)
         dtype = capi.DTYPE_F64 if dname == "float64" else capi.DTYPE_F32
         p = (lambda t: ctypes.c_void_p(t.data_ptr())) if self.rank == root else (lambda t: None)
         capi.check(lib, ctx, lib.bhb200_dist_setup_square(
@@ -414,6 +414,32 @@ class NcclRowBlockSpGEMM:
         self.engine._order_after_producers()
         capi.check(lib, ctx, lib.bhb200_dist_spgemm(ctx))
         return int(lib.bhb200_get_nnzC(ctx)), None, None
+
+    def _operands(self):
+        lib, ctx = self.engine.lib, self.engine.ctx
+        dims = (ctypes.c_int32 * 6)()
+        ptr = [ctypes.c_void_p() for _ in range(6)]
+        capi.check(lib, ctx, lib.bhb200_get_operands_device(ctx, dims, *(ctypes.byref(x) for x in ptr)))
+        m, k, n, nnzA, nnzB, dtype = (int(x) for x in dims)
+        vt = "<f8" if dtype == capi.DTYPE_F64 else "<f4"
+        capi.check(lib, ctx, lib.bhb200_synchronize(ctx))
+
+        def view(p, numel, ts):
+            if numel == 0:
+                return torch.empty(0, dtype={"<i4": torch.int32, "<f8": torch.float64, "<f4": torch.float32}[ts], device=self.device)
+            return torch.as_tensor(_DevicePtr(p.value, numel, ts), device=self.device)
+        A = (view(ptr[0], m + 1, "<i4"), view(ptr[1], nnzA, "<i4"), view(ptr[2], nnzA, vt))
+        B = (view(ptr[3], k + 1, "<i4"), view(ptr[4], nnzB, "<i4"), view(ptr[5], nnzB, vt))
+        return A, B
+
+    @property
+    def A(self):
+        """This rank's row block of A as the library holds it (views of device memory)."""
+        return self._operands()[0]
+
+    @property
+    def B(self):
+        return self._operands()[1]
 
     def layout(self):
         """(row_begin, row_end, nnz_offset, nnz_total) of this rank -- copies nranks int64 from the device."""

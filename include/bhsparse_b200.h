@@ -120,6 +120,13 @@ BHB200_API int bhb200_init_data_f32(bhb200_ctx *ctx, int m, int k, int n,
  * the reference driver's stock workloads set it up, main.cu:32-51): they are uploaded once and both
  * operands share the device copy.  bhb200_update_values_* then takes one set of values. */
 BHB200_API int bhb200_operands_aliased(const bhb200_ctx *ctx);
+/* The operands as the library holds them on the device (borrowed views, valid until the next
+ * init_data / dist_setup / free_mem): dims = {m, k, n, nnzA, nnzB, dtype}.  After
+ * bhb200_dist_setup_square this is the rank's row block of A and its replica of B.  Any pointer may
+ * be NULL. */
+BHB200_API int bhb200_get_operands_device(const bhb200_ctx *ctx, int32_t *dims, const int32_t **rowptrA,
+                                          const int32_t **colA, const void **valA, const int32_t **rowptrB,
+                                          const int32_t **colB, const void **valB);
 /* Same, but the six arrays are DEVICE pointers on the context's device and are
  * borrowed (not copied, not freed) until bhb200_free_mem: the device-resident
  * operand API of SURVEY.md 8(f).3, used by the multi-GPU row-block driver. */

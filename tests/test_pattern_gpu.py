@@ -112,3 +112,47 @@ def test_pattern_switch_and_reuse(monkeypatch):
     assert_csr_equal((rowptrC, col, val), want2, what="numeric reuse in pattern mode")
     bh.free_mem()
     bh.freePlatform()
+
+
+def test_cached_plan_is_verified_on_every_call(monkeypatch):
+    """A context reuses the plan of its previous product without the detection pass; every entry is
+    checked against it, and operands with other diagonals (or none) fall back to the full detection /
+    the general path.  Same results with BHB200_PATTERN=detect (detection on every call)."""
+    seq = [gen.poisson27pt(10, 11, 12), gen.poisson27pt(10, 11, 12),        # same plan twice
+           gen.poisson27pt(9, 13, 12),                                      # other strides: other offsets
+           gen.poisson7pt(12, 12, 12),                                      # fewer diagonals
+           gen.diagonals(1700, 1700, [-40, -1, 0, 1, 2, 40], keep=0.8),     # subset rows
+           gen.rmat(10, 8),                                                 # no structure at all
+           gen.poisson5pt(40, 41)]                                          # and back
+    want_mode = [1, 1, 1, 1, 1, 0, 1]
+    for env in (None, "detect"):
+        if env:
+            monkeypatch.setenv("BHB200_PATTERN", env)
+        platforms = [False] * NUM_PLATFORMS
+        platforms[BHSPARSE_CUDA] = True
+        bh = bhsparse()
+        assert bh.initPlatform(platforms) == 0
+        for A, mode in zip(seq, want_mode):
+            rowptrC = np.zeros(A.rows + 1, dtype=np.int32)
+            assert bh.initData(A.rows, A.cols, A.cols, A.nnz, A.val, A.rowptr, A.col, A.nnz, A.val, A.rowptr, A.col, rowptrC) == 0
+            assert bh.spgemm() == 0, bh.last_error()
+            assert bh.stats()["pattern_mode"] == mode
+            n = bh.get_nnzC()
+            col, val = np.empty(n, np.int32), np.empty(n, np.float64)
+            assert bh.get_C(col, val) == 0
+            assert_csr_equal((rowptrC, col, val), _oracle(A, A), what=f"sequence step ({env})")
+        # A and B with different diagonal sets after a square product (the cached lists must not be mixed up)
+        A = gen.diagonals(900, 900, [-3, 0, 5])
+        B = gen.diagonals(900, 900, [-7, -1, 0, 2, 11], value_seed=4)
+        rowptrC = np.zeros(A.rows + 1, dtype=np.int32)
+        assert bh.initData(A.rows, A.cols, B.cols, A.nnz, A.val, A.rowptr, A.col, B.nnz, B.val, B.rowptr, B.col, rowptrC) == 0
+        assert bh.spgemm() == 0 and bh.stats()["pattern_mode"] == 1
+        n = bh.get_nnzC()
+        col, val = np.empty(n, np.int32), np.empty(n, np.float64)
+        assert bh.get_C(col, val) == 0
+        assert_csr_equal((rowptrC, col, val), _oracle(A, B), what="A != B after A == B")
+        assert bh.spgemm() == 0                         # same operands again: speculative hit
+        assert bh.get_C(col, val) == 0
+        assert_csr_equal((rowptrC, col, val), _oracle(A, B), what="A != B again")
+        bh.free_mem()
+        bh.freePlatform()
