@@ -29,10 +29,11 @@ SOURCES = [
     "stage_pattern.cu",
     "pattern_plan.cu",
     "dist_nccl.cu",
+    "stage_bucket.cu",
     "stage_numeric_f32.cu",
     "stage_numeric_f64.cu",
 ]
-HEADERS = ["common.cuh", "stage_numeric.cuh", "stage_range.cuh", "stage_range_vec.cuh", "stage_pattern.cuh", "pattern_plan.h", "context.h", os.path.join(INCLUDE, "bhsparse_b200.h")]
+HEADERS = ["common.cuh", "stage_numeric.cuh", "stage_range.cuh", "stage_range_vec.cuh", "stage_pattern.cuh", "pattern_plan.h", "context.h", "stage_bucket.cuh", os.path.join(INCLUDE, "bhsparse_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -38,7 +38,7 @@ EXPORTED = [
     "bhb200_update_values_f64", "bhb200_update_values_f32", "bhb200_spgemm_numeric",
     "bhb200_dist_unique_id", "bhb200_dist_init", "bhb200_dist_setup_square", "bhb200_dist_spgemm",
     "bhb200_dist_get_layout", "bhb200_dist_get_block_products", "bhb200_dist_get_global_rowptr_device",
-    "bhb200_dist_broadcast_ms", "bhb200_dist_finalize",
+    "bhb200_dist_broadcast_ms", "bhb200_dist_finalize", "bhb200_pattern_plan_probe",
 ]
 DIST_ID_BYTES = 128
 
@@ -137,6 +137,7 @@ def load(build_if_missing: bool = False):
     L.bhb200_dist_get_global_rowptr_device.argtypes = [ctxp, POINTER(c_void_p)]
     L.bhb200_dist_broadcast_ms.argtypes = [ctxp, POINTER(c_float)]
     L.bhb200_dist_finalize.argtypes = [ctxp]
+    L.bhb200_pattern_plan_probe.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     for name in EXPORTED:
         f = getattr(L, name)
         if f.restype is c_int:  # default

@@ -570,6 +570,14 @@ cudaError_t launch_num_direct_f32(const LaunchCtx &lc, int cap, int G, const int
                                   DirectOut d);
 cudaError_t launch_num_direct_f64(const LaunchCtx &lc, int cap, int G, const int *queue, int count, Csr A, Csr B,
                                   DirectOut d);
+// bucket-sort ESC for rows that barely compress (stage_bucket.cuh): wide direct bins, cap >= 512
+cudaError_t launch_num_bucket_f32(const LaunchCtx &lc, int cap, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                  const unsigned *cdf, int cdf_shift);
+cudaError_t launch_num_bucket_f64(const LaunchCtx &lc, int cap, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                  const unsigned *cdf, int cdf_shift);
+// column CDF of the intermediate products (stage_bucket.cu): colcountA [k+1] ints, hist [4096] u64, cdf [4097] u32
+cudaError_t launch_build_cdf(const LaunchCtx &lc, int m, int k, int n, int nnzA, Csr A, Csr B, int *colcountA,
+                             unsigned long long *hist, unsigned *cdf, int *shift_out);
 cudaError_t launch_copy_ct(const LaunchCtx &lc, int dtype, const int *queue, int count, const int64_t *rowoff,
                            const long long *ct_off, const int *ctcol, const void *ctval, int *colC, void *valC);
 cudaError_t launch_num_large_f32(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B,

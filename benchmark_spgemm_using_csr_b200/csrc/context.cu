@@ -5,7 +5,9 @@
 // 300-byte counter block (bin sizes; nnz(C)) -- the reference has >= 8 blocking copies of
 // O(m) data plus 3 per merge round.
 #include "context.h"
+#include "stage_bucket.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -443,6 +445,10 @@ int bhb200_create(bhb200_ctx **out, int device)
         ctx->pattern_enable = strcmp(pm, "off") != 0;
         ctx->pattern_speculate = strcmp(pm, "detect") != 0;   // "detect": run the offset-set pass on every call
     }
+    if (const char *be = getenv("BHB200_BUCKET")) {
+        ctx->bucket_enable = strcmp(be, "off") != 0;
+        if (atoi(be) >= 512) ctx->bucket_min_cap = atoi(be);   // BHB200_BUCKET=<capacity>: smallest capacity that takes the bucket kernel
+    }
     if (const char *dc = getenv("BHB200_DEBUG_DEVICE_CAP")) ctx->device_cap = (size_t)atoll(dc);
     if (const char *dm = getenv("BHB200_DIRECT")) {
         ctx->direct_mode = strcmp(dm, "off") != 0;
@@ -473,7 +479,7 @@ int bhb200_free_mem(bhb200_ctx *ctx)
     ctx->plan = PatternPlan();
     ctx->last_pattern = false;
     DevBuf *bufs[] = {&ctx->pat_sets, &ctx->pat_ta, &ctx->pat_tb, &ctx->pat_maskB, &ctx->pat_outmask, &ctx->pat_tables, &ctx->pat_fullbits,
-                      &ctx->ct_off, &ctx->ct_col, &ctx->ct_val, &ctx->retry_q,
+                      &ctx->cdf_colcount, &ctx->cdf_hist, &ctx->cdf_tab, &ctx->ct_off, &ctx->ct_col, &ctx->ct_val, &ctx->retry_q,
                       &ctx->brange, &ctx->rlo, &ctx->rspan, &ctx->wl_off, &ctx->wl_cnt, &ctx->wl_idx, &ctx->wl_bits,
                       &ctx->prod, &ctx->rc, &ctx->queue, &ctx->rowoff64, &ctx->rowptr32, &ctx->blocksums,
                       &ctx->counters, &ctx->bitmap, &ctx->prefix, &ctx->colC, &ctx->valC};
@@ -775,6 +781,22 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     st.direct_bin_mask = (int64_t)spec_mask;
     CU(cudaEventRecord(ctx->ev[1], s), "event");
 
+    // wide bins with 512+ entries per row: bucket-sort kernels, which need the column CDF of the products
+    bool use_bucket = false;
+    int cdf_shift = 0;
+    if (ctx->bucket_enable && spec_mask) {
+        for (int b = SB_G512; b <= SB_B8192; ++b) use_bucket |= ((spec_mask >> b) & 1u) && spec_wide[b] && spec_cap[b] >= ctx->bucket_min_cap;
+        if (use_bucket && (ctx->cdf_colcount.reserve(((size_t)ctx->k + 1) * 4, &ctx->dev_bytes) != cudaSuccess ||
+                           ctx->cdf_hist.reserve((size_t)CDF_KNOTS * 8, &ctx->dev_bytes) != cudaSuccess ||
+                           ctx->cdf_tab.reserve((size_t)(CDF_KNOTS + 1) * 4, &ctx->dev_bytes) != cudaSuccess)) {
+            cudaGetLastError();
+            use_bucket = false;
+        }
+        if (use_bucket)
+            CU(launch_build_cdf(lc, ctx->m, ctx->k, ctx->n, ctx->nnzA, ctx->A, ctx->B, ctx->cdf_colcount.as<int>(),
+                                ctx->cdf_hist.as<unsigned long long>(), ctx->cdf_tab.as<unsigned>(), &cdf_shift),
+               "column CDF");
+    }
     // ---- stage 2: symbolic, one launch per non-empty bin (direct-mode bins: the numeric kernel itself) ----
     memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
     if (hc.sym_bin[SB_ESC] > 0) CU(stamp(ctx, 0, SB_ESC), "event");
@@ -795,7 +817,14 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                     d.p_hi = pass == 0 ? spec_cap[b] / 2 : 0x7fffffff;
                     if (pass == 0) cap = spec_cap[b] / 2;
                 }
-                if (ctx->dtype == BHB200_DTYPE_F64)
+                if (spec_wide[b] && use_bucket && cap >= ctx->bucket_min_cap) {
+                    if (ctx->dtype == BHB200_DTYPE_F64)
+                        CU(launch_num_bucket_f64(lc, cap, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift),
+                           "bucket numeric f64");
+                    else
+                        CU(launch_num_bucket_f32(lc, cap, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift),
+                           "bucket numeric f32");
+                } else if (ctx->dtype == BHB200_DTYPE_F64)
                     CU(launch_num_direct_f64(lc, cap, spec_wide[b] ? 32 : G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d),
                        "direct numeric f64");
                 else
@@ -1023,6 +1052,37 @@ int bhb200_get_operands_device(const bhb200_ctx *ctx, int32_t *dims, const int32
     if (rowptrB) *rowptrB = ctx->B.rowptr;
     if (colB) *colB = ctx->B.col;
     if (valB) *valB = ctx->B.val;
+    return BHB200_SUCCESS;
+}
+
+int bhb200_pattern_plan_probe(const int32_t *offsA, int nA, const int32_t *offsB, int nB, int value_size, int32_t *info,
+                              uint8_t *position, int32_t *offsC)
+{
+    // host-only: the plan the diagonal-pattern mode would build for these offset sets (tests, tools)
+    if (!offsA || !offsB || !info || (value_size != 4 && value_size != 8)) return BHB200_ERR_INVALID;
+    PatternPlan plan;
+    if (!build_pattern_plan(offsA, nA, offsB, nB, value_size, plan)) {
+        info[0] = 0;
+        return BHB200_SUCCESS;
+    }
+    const int nb = value_size == 8 ? 16 : 32;
+    const unsigned char *mphys = plan.blob.data() + plan.off_mphys;
+    int cost = 0, groups = 0;
+    for (int ja = 0; ja < nA; ++ja)
+        for (int j0 = 0; j0 < nB; j0 += nb) {
+            int cnt[32] = {0}, mx = 0;
+            for (int jb = j0; jb < nB && jb < j0 + nb; ++jb) mx = std::max(mx, ++cnt[mphys[(size_t)ja * nB + jb] % nb]);
+            cost += mx;
+            ++groups;
+        }
+    info[0] = 1;
+    info[1] = plan.nD;
+    info[2] = plan.nw;
+    info[3] = plan.acc_len;
+    info[4] = cost;      // shared-memory wavefronts of one accumulate pass over all (A offset, lane group) pairs
+    info[5] = groups;    // ... and its conflict-free minimum
+    if (position) memcpy(position, mphys, (size_t)nA * nB);
+    if (offsC) memcpy(offsC, plan.blob.data() + plan.off_dcol, (size_t)plan.nD * 4);
     return BHB200_SUCCESS;
 }
 

@@ -207,6 +207,15 @@ int bhb200_dist_init(bhb200_ctx *ctx, int rank, int nranks, const void *id)
     DCU(cudaHostAlloc((void **)&d->h_counts, sizeof(long long) * MAX_RANKS, cudaHostAllocDefault), "pinned");
     DCU(d->d_part.reserve(sizeof(Partition), &ctx->dev_bytes), "alloc partition record");
     DCU(d->d_counts.reserve(sizeof(long long) * (MAX_RANKS + 1), &ctx->dev_bytes), "alloc counts");
+    // NCCL builds its rings / NVLS trees at the first collective of each kind on a communicator (hundreds
+    // of milliseconds): do that here, on both streams that will carry traffic, not inside the first set-up
+    long long *counts = d->d_counts.as<long long>();
+    DCU(cudaMemsetAsync(counts, 0, sizeof(long long) * (MAX_RANKS + 1), ctx->stream), "zero counts");
+    DNC(nccl().AllGather(counts + MAX_RANKS, counts, 1, ncclInt64, d->comm, ctx->stream), "ncclAllGather(warm-up)");
+    DNC(nccl().Broadcast(d->d_part.p, d->d_part.p, sizeof(Partition), ncclInt8, 0, d->comm, ctx->stream), "ncclBroadcast(warm-up)");
+    DCU(cudaStreamSynchronize(ctx->stream), "NCCL warm-up");
+    DNC(nccl().Broadcast(d->d_part.p, d->d_part.p, sizeof(Partition), ncclInt8, 0, d->comm, d->val_stream), "ncclBroadcast(warm-up)");
+    DCU(cudaStreamSynchronize(d->val_stream), "NCCL warm-up");
     return BHB200_SUCCESS;
 }
 

@@ -1,0 +1,178 @@
+// stage_bucket.cuh -- expand / bucket-sort / compress for rows that barely compress.
+//
+// R-MAT rows (BASELINE configs 3 and 5): nnz(C_i) is within a fraction of a percent of the row's
+// intermediate products, so hashing buys nothing and the work is a sort of p (column, value) pairs.
+// The hash kernels sort with a bitonic network -- O(log^2 p) compare-exchanges per key, ~200 of their
+// ~240 instructions per product at p = 1024 (profiles/r02_notes.md).  This kernel sorts in O(1) passes:
+//
+//   * a MONOTONE bucket function  bucket(c) = floor(F(c) * NB),  F = the cumulative distribution of the
+//     columns of all intermediate products of the whole multiplication (a 4096-knot piecewise-linear
+//     table built once per product by k_cdf_*: every entry (k, c) of B weighted by the number of entries
+//     of A in column k).  Under F the products of a row spread almost evenly over the buckets, whatever
+//     the skew of the matrix (R-MAT: a third of all products fall into 1 % of the column range);
+//   * pass 1 counts the products of the row per bucket (shared-memory integer atomics), a CTA-wide scan
+//     turns the counts into segments, pass 2 scatters (column, a*b) into them;
+//   * one thread per bucket sorts its few entries by insertion and merges equal columns; the buckets are
+//     in column order, so the row is sorted; a second scan gives the compacted positions.
+//
+// It plays the role of the reference's EM_mergepath rounds (bhsparse_cuda.h:1902-2157) for these rows.
+// One CTA per row; direct (single-pass) mode only: the row is staged at ct_base + q*ct_stride, its
+// length goes to rc[], k_copy_ct moves it to its final place after the scan.
+#pragma once
+#include "common.cuh"
+
+namespace bhb {
+
+constexpr int CDF_BITS = 12;
+constexpr int CDF_KNOTS = 1 << CDF_BITS;   // cdf[0 .. CDF_KNOTS], cdf[i] = F(i << shift) scaled to 2^32
+
+struct ColumnCdf {
+    const unsigned *cdf;   // [CDF_KNOTS + 1], non-decreasing, cdf[0] = 0
+    int shift;             // column >> shift < CDF_KNOTS
+};
+
+__device__ __forceinline__ unsigned cdf_eval(const ColumnCdf &f, const int c)
+{
+    const int i = c >> f.shift;
+    const unsigned lo = __ldg(f.cdf + i), hi = __ldg(f.cdf + i + 1);
+    const unsigned frac = (unsigned)c & ((1u << f.shift) - 1u);
+    return lo + (unsigned)(((unsigned long long)(hi - lo) * frac) >> f.shift);
+}
+
+// exclusive scan of a[0..n) in place by the whole CTA; returns the total.  scratch: 33 ints.
+template <int THREADS>
+__device__ __forceinline__ int cta_exclusive_scan(int *a, const int n, int *scratch)
+{
+    const int per = (n + THREADS - 1) / THREADS;
+    const int b0 = (int)threadIdx.x * per, b1 = min(b0 + per, n);
+    int mine = 0;
+    for (int i = b0; i < b1; ++i) mine += a[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < THREADS / 32) ? scratch[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(FULL, w, d);
+            if (lane >= d) w += y;
+        }
+        scratch[lane] = w;   // inclusive warp totals; scratch[THREADS/32 - 1] = grand total
+    }
+    __syncthreads();
+    int run = (warp ? scratch[warp - 1] : 0) + incl - mine;
+    const int total = scratch[THREADS / 32 - 1];
+    for (int i = b0; i < b1; ++i) {
+        const int v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    __syncthreads();
+    return total;
+}
+
+template <typename VT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_num_bucket(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA, const int *__restrict__ colA,
+             const VT *__restrict__ valA, const int *__restrict__ rowptrB, const int *__restrict__ colB,
+             const VT *__restrict__ valB, const ColumnCdf cdf, const int cap, const int nb, int *__restrict__ rc,
+             long long *__restrict__ ct_off, int *__restrict__ ctcol, VT *__restrict__ ctval, const long long ct_base,
+             const int *__restrict__ prod, const int p_lo, const int p_hi, const int ct_stride)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VT *vals = reinterpret_cast<VT *>(smem_raw);                              // [cap]
+    int *keys = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(VT));   // [cap]
+    int *cnt = keys + cap;                                                    // [nb]  bucket counts -> segment ends
+    int *ocnt = cnt + nb;                                                     // [nb + 1] merged counts -> output positions
+    int *scratch = ocnt + nb + 1;                                             // [34]: scan scratch + the B-row counter
+    const int lane = threadIdx.x & 31;
+
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int row = queue[q];
+        const int p = prod[row];
+        if (p <= p_lo || p > p_hi) continue;   // CTA-uniform
+        for (int i = threadIdx.x; i < nb; i += THREADS) cnt[i] = 0;
+        if (threadIdx.x == 0) scratch[33] = 0;
+        __syncthreads();
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        // ---- pass 1: products per bucket (warps take B rows from a shared counter, see k_num_block) ----
+        for (int j = a0 + take_next(&scratch[33], lane); j < a1; j = a0 + take_next(&scratch[33], lane)) {
+            const int k = colA[j];
+            const int bs = rowptrB[k], be = rowptrB[k + 1];
+            for (int e = bs + lane; e < be; e += 32)
+                atomicAdd(&cnt[__umulhi(cdf_eval(cdf, colB[e]), (unsigned)nb)], 1);
+        }
+        __syncthreads();
+        cta_exclusive_scan<THREADS>(cnt, nb, scratch);   // cnt[b] = first slot of bucket b
+        if (threadIdx.x == 0) scratch[33] = 0;
+        __syncthreads();
+        // ---- pass 2: scatter (column, a*b) into the segments; afterwards cnt[b] = END of bucket b ----
+        for (int j = a0 + take_next(&scratch[33], lane); j < a1; j = a0 + take_next(&scratch[33], lane)) {
+            const int k = colA[j];
+            const VT av = valA[j];
+            const int bs = rowptrB[k], be = rowptrB[k + 1];
+            for (int e = bs + lane; e < be; e += 32) {
+                const int c = colB[e];
+                const int slot = atomicAdd(&cnt[__umulhi(cdf_eval(cdf, c), (unsigned)nb)], 1);
+                keys[slot] = c;
+                vals[slot] = av * valB[e];
+            }
+        }
+        __syncthreads();
+        // ---- per bucket: insertion sort by column, equal columns merged.  (Measured and dropped: one ENTRY
+        // per thread ranking itself inside its bucket, rows permuted through registers -- 64 registers and
+        // twice the threads per row made every bin slower, profiles/r02_notes.md.) ----
+        for (int b = threadIdx.x; b < nb; b += THREADS) {
+            const int s = b ? cnt[b - 1] : 0, e = cnt[b];
+            for (int i = s + 1; i < e; ++i) {
+                const int kc = keys[i];
+                const VT kv = vals[i];
+                int j = i - 1;
+                while (j >= s && keys[j] > kc) {
+                    keys[j + 1] = keys[j];
+                    vals[j + 1] = vals[j];
+                    --j;
+                }
+                keys[j + 1] = kc;
+                vals[j + 1] = kv;
+            }
+            int w = s;
+            for (int i = s; i < e; ++i) {
+                if (i > s && keys[i] == keys[w - 1]) {
+                    vals[w - 1] += vals[i];
+                } else {
+                    keys[w] = keys[i];
+                    vals[w] = vals[i];
+                    ++w;
+                }
+            }
+            ocnt[b] = w - s;
+        }
+        if (threadIdx.x == 0) ocnt[nb] = 0;
+        __syncthreads();
+        const int total = cta_exclusive_scan<THREADS>(ocnt, nb + 1, scratch);   // ocnt[b] = output position of bucket b
+        // ---- emit ----
+        const long long o = ct_base + (long long)q * ct_stride;
+        if (threadIdx.x == 0) {
+            rc[row] = total;
+            ct_off[row] = o;
+        }
+        for (int b = threadIdx.x; b < nb; b += THREADS) {
+            const int s = b ? cnt[b - 1] : 0;
+            const int o0 = ocnt[b], n = ocnt[b + 1] - o0;
+            for (int i = 0; i < n; ++i) {
+                ctcol[o + o0 + i] = keys[s + i];
+                ctval[o + o0 + i] = vals[s + i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace bhb

@@ -20,6 +20,9 @@
 //      final C row with red.global.add -- no spill, no re-allocation, no sort.
 #pragma once
 #include "common.cuh"
+#include "stage_bucket.cuh"
+
+#include <cstdlib>
 
 namespace bhb {
 
@@ -785,6 +788,41 @@ static cudaError_t launch_num_direct_t(const LaunchCtx &lc, int cap, int G, cons
                       : launch_num_direct_g<VT, 32, 8, 4>(lc, queue, count, A, B, d);
     default: return cudaErrorInvalidValue;
     }
+}
+
+template <typename VT, int THREADS>
+static cudaError_t launch_num_bucket_tt(const LaunchCtx &lc, int cap, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                        ColumnCdf cdf)
+{
+    // buckets per row: cap / BHB200_BUCKET_DIV (default 4: about four entries per bucket for a full row)
+    static const int div = [] { const char *e = getenv("BHB200_BUCKET_DIV"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }();
+    const int nb = cap / div < 32 ? 32 : cap / div;
+    const size_t smem = (size_t)cap * (sizeof(VT) + 4) + (size_t)(2 * nb + 1 + 34) * 4;
+    auto kern = k_num_bucket<VT, THREADS>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    long long blocks = count;
+    const long long lim = (long long)lc.sm_count * resident_blocks(kern, THREADS, smem);
+    if (blocks > lim) blocks = lim;
+    ++*lc.launches;
+    kern<<<(int)blocks, THREADS, smem, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
+                                                    (const VT *)B.val, cdf, cap, nb, d.rc, d.ct_off, d.ctcol, (VT *)d.ctval,
+                                                    d.ct_base, d.prod, d.p_lo, d.p_hi, d.ct_stride ? d.ct_stride : cap);
+    return cudaGetLastError();
+}
+
+// rows of the queue with p_lo < products <= p_hi <= cap, staged ct_stride apart (wide direct bins)
+template <typename VT>
+static cudaError_t launch_num_bucket_t(const LaunchCtx &lc, int cap, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                       ColumnCdf cdf)
+{
+    if (count <= 0) return cudaSuccess;
+    if (cap <= 1024) return launch_num_bucket_tt<VT, 128>(lc, cap, queue, count, A, B, d, cdf);
+    if (cap <= 2048) return launch_num_bucket_tt<VT, 256>(lc, cap, queue, count, A, B, d, cdf);
+    if (cap <= 4096) return launch_num_bucket_tt<VT, 512>(lc, cap, queue, count, A, B, d, cdf);
+    return launch_num_bucket_tt<VT, 1024>(lc, cap, queue, count, A, B, d, cdf);
 }
 
 template <typename VT>

@@ -32,4 +32,10 @@ cudaError_t launch_num_direct_f32(const LaunchCtx &lc, int cap, int G, const int
     return launch_num_direct_t<float>(lc, cap, G, queue, count, A, B, d);
 }
 
+cudaError_t launch_num_bucket_f32(const LaunchCtx &lc, int cap, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                  const unsigned *cdf, int cdf_shift)
+{
+    return launch_num_bucket_t<float>(lc, cap, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift});
+}
+
 }  // namespace bhb

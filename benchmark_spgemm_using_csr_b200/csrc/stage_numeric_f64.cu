@@ -43,4 +43,10 @@ cudaError_t launch_copy_ct(const LaunchCtx &lc, int dtype, const int *queue, int
                                            (float *)valC, 64.0);
 }
 
+cudaError_t launch_num_bucket_f64(const LaunchCtx &lc, int cap, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                  const unsigned *cdf, int cdf_shift)
+{
+    return launch_num_bucket_t<double>(lc, cap, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift});
+}
+
 }  // namespace bhb

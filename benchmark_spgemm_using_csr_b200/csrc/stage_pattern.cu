@@ -79,7 +79,11 @@ __global__ void __launch_bounds__(256) k_offset_set(const int rows, const int *_
                     const int old = atomicCAS(&s_slot[h], PAT_EMPTY, d);
                     if (old == PAT_EMPTY) {
                         // first sighting in this CTA
-                        if (atomicAdd(&s_count, 1) + 1 > PAT_MAX_OFFS) {
+                        // (an unstructured matrix: some CTA overflows within microseconds; the others must not
+                        // queue up on the global set's atomics -- measured 260 us on a random 4M-row matrix before)
+                        if (*(volatile int *)&set->overflow) {
+                            *(volatile int *)&s_stop = 1;
+                        } else if (atomicAdd(&s_count, 1) + 1 > PAT_MAX_OFFS) {
                             set->overflow = 1;
                             *(volatile int *)&s_stop = 1;
                         } else {

@@ -229,6 +229,16 @@ BHB200_API int bhb200_dist_get_global_rowptr_device(bhb200_ctx *ctx, const int64
 BHB200_API int bhb200_dist_broadcast_ms(bhb200_ctx *ctx, float *ms);
 BHB200_API int bhb200_dist_finalize(bhb200_ctx *ctx);
 
+/* Host-only probe of the diagonal-pattern mode (no reference counterpart; no GPU needed): the plan
+ * the library would build for operands whose entries sit on the diagonals offsA (nA values of
+ * column - row) and offsB.  info[0] = 1 if the mode applies (at most 64 diagonals per operand and 256
+ * in the product), then info[1..5] = diagonals of C, mask words per row, accumulator length,
+ * shared-memory wavefronts of one pass over all (A diagonal, lane group) pairs with the chosen
+ * accumulator layout, and their conflict-free minimum.  position (nA*nB bytes, optional): accumulator
+ * slot of product (ja, jb), diagonals in ascending order; offsC (<= 256 ints, optional): diagonals of C. */
+BHB200_API int bhb200_pattern_plan_probe(const int32_t *offsA, int nA, const int32_t *offsB, int nB, int value_size,
+                                         int32_t *info, uint8_t *position, int32_t *offsC);
+
 /* bhb200_free_mem replaces bhsparse::free_mem (bhsparse.h:150-177,
  * bhsparse_cuda.h:121-149): releases operands, results and workspace. */
 BHB200_API int bhb200_free_mem(bhb200_ctx *ctx);
