@@ -125,6 +125,7 @@ struct Counters {
     int bad_B;                     // a row of B is not strictly ascending / has a column outside [0, n)
     int bad_A;                     // a column of A is outside [0, k)
     int pat_miss;                  // pattern mode: an entry's offset is not in the (cached) offset lists
+    int a_col_range[2];            // pattern mode: {max column of A, INT_MAX - min column of A} (which rows of B matter)
     int sym_bin[MAX_BINS];
     int num_bin[MAX_BINS];
     int sym_cursor[MAX_BINS];
@@ -132,6 +133,8 @@ struct Counters {
     int sample_max[MAX_BINS];      // direct mode: largest nnz(C_i) among the sampled rows of a symbolic bin
     int retry_cnt[MAX_BINS];       // direct mode: rows of a bin that overflowed their speculated capacity
     unsigned long long sample_sum[MAX_BINS];   // direct mode: sum of nnz(C_i) over the sampled rows
+    unsigned long long sym_bin_products[MAX_BINS];   // intermediate products per symbolic bin (sizes the heavy rows' staging)
+    unsigned long long heavy_cursor;                 // bump allocator of k_num_bucket_heavy's staging
     unsigned long long num_bin_products[MAX_BINS];
     unsigned long long num_bin_nnzc[MAX_BINS];
     unsigned long long num_bin_nnza[MAX_BINS];
@@ -575,6 +578,11 @@ cudaError_t launch_num_bucket_f32(const LaunchCtx &lc, int cap, const int *queue
                                   const unsigned *cdf, int cdf_shift);
 cudaError_t launch_num_bucket_f64(const LaunchCtx &lc, int cap, const int *queue, int count, Csr A, Csr B, DirectOut d,
                                   const unsigned *cdf, int cdf_shift);
+// heavy rows (more products than fit on chip): sliced bucket sort, staged at ct_base + bump(cursor, products)
+cudaError_t launch_num_bucket_heavy_f32(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                        const unsigned *cdf, int cdf_shift, unsigned long long *cursor);
+cudaError_t launch_num_bucket_heavy_f64(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                        const unsigned *cdf, int cdf_shift, unsigned long long *cursor);
 // column CDF of the intermediate products (stage_bucket.cu): colcountA [k+1] ints, hist [4096] u64, cdf [4097] u32
 cudaError_t launch_build_cdf(const LaunchCtx &lc, int m, int k, int n, int nnzA, Csr A, Csr B, int *colcountA,
                              unsigned long long *hist, unsigned *cdf, int *shift_out);

@@ -328,19 +328,23 @@ int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab, bool specula
     }
     if (!had_tables)
         CU(cudaMemcpyAsync(ctx->pat_tables.p, plan.blob.data(), need_tab, cudaMemcpyHostToDevice, s), "H2D pattern tables");
-    const PatTables t = pattern_tables(plan, ctx->pat_tables.as<unsigned char>());
+    PatTables t = pattern_tables(plan, ctx->pat_tables.as<unsigned char>());
+    t.fullbits = ctx->pat_fullbits.as<unsigned>();
     unsigned char *tb = ctx->pat_tb.as<unsigned char>();
     unsigned char *ta = same_ab ? tb : ctx->pat_ta.as<unsigned char>();
     int *rcnt = ctx->rc.as<int>();
     Counters *d_ctr = ctx->counters.as<Counters>();
     const long long spanA = (long long)plan.DA.back() - plan.DA.front() + 1, spanB = (long long)plan.DB.back() - plan.DB.front() + 1;
-    CU(launch_pat_codes(lc, ctx->k, ctx->n, ctx->B.rowptr, ctx->B.col, t.offsB, t.nDB, spanB, tb, ctx->pat_maskB.as<unsigned long long>(),
-                        &d_ctr->bad_B, &d_ctr->pat_miss, t.fullB, ctx->pat_fullbits.as<unsigned>()),
-       "pattern codes of B");
+    // A first (when it is not B itself): its column range tells which rows of B this product reads -- in a
+    // multi-GPU row block that is a fraction of B, and only those rows are coded and checked
     if (!same_ab)
         CU(launch_pat_codes(lc, ctx->m, ctx->k, ctx->A.rowptr, ctx->A.col, t.offsA, t.nDA, spanA, ta, nullptr, &d_ctr->bad_A,
-                            &d_ctr->pat_miss, 0ull, nullptr),
+                            &d_ctr->pat_miss, 0ull, nullptr, d_ctr->a_col_range, nullptr),
            "pattern codes of A");
+    CU(launch_pat_codes(lc, ctx->k, ctx->n, ctx->B.rowptr, ctx->B.col, t.offsB, t.nDB, spanB, tb, ctx->pat_maskB.as<unsigned long long>(),
+                        &d_ctr->bad_B, &d_ctr->pat_miss, t.fullB, ctx->pat_fullbits.as<unsigned>(), nullptr,
+                        same_ab ? nullptr : d_ctr->a_col_range),
+       "pattern codes of B");
     CU(cudaEventRecord(ctx->ev[1], s), "event");
     // exact nnz(C_i) from the offset masks; also the per-row product counts (compute_nnzCt,
     // bhsparse_cuda.h:210-237) and their total -- the general path's stage-1 kernels are not run
@@ -445,6 +449,7 @@ int bhb200_create(bhb200_ctx **out, int device)
         ctx->pattern_enable = strcmp(pm, "off") != 0;
         ctx->pattern_speculate = strcmp(pm, "detect") != 0;   // "detect": run the offset-set pass on every call
     }
+    if (const char *bh = getenv("BHB200_BUCKET_HEAVY")) ctx->bucket_heavy = strcmp(bh, "off") != 0;
     if (const char *be = getenv("BHB200_BUCKET")) {
         ctx->bucket_enable = strcmp(be, "off") != 0;
         if (atoi(be) >= 512) ctx->bucket_min_cap = atoi(be);   // BHB200_BUCKET=<capacity>: smallest capacity that takes the bucket kernel
@@ -690,6 +695,8 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     unsigned spec_mask = 0;
     int spec_cap[MAX_BINS] = {0};
     bool spec_wide[MAX_BINS] = {false};
+    bool spec_heavy[MAX_BINS] = {false};   // rows beyond the on-chip tables: sliced bucket sort (k_num_bucket_heavy)
+    long long heavy_base = 0;
     long long spec_base[MAX_BINS] = {0};
     long long ct_entries = 0;
     const int SAMPLE_STRIDE = 64;
@@ -740,6 +747,28 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                 spec_mask |= 1u << b;
             }
         }
+        // rows with more products than the on-chip tables hold follow the largest sampled bin: if that one
+        // does not compress they run once through the sliced bucket sort, staged at their product count
+        // (BHB200_DEBUG_FORCE_HEAVY: tests send them there whatever the sample says)
+        bool top_wide = getenv("BHB200_DEBUG_FORCE_HEAVY") != nullptr;
+        for (int b = SB_B8192; b >= SB_G128 && !top_wide; --b)
+            if (hc.sym_bin[b] > 0) {
+                top_wide = ((spec_mask >> b) & 1u) && spec_wide[b];
+                break;
+            }
+        // (measured, profiles/r02_notes.md: the sliced bucket sort runs at ~13 products/ns whatever n is; the
+        // two-pass tables + global column bitmap at 16 products/ns for n = 2 M columns, 14 at 4 M, 7 at 16.8 M)
+        const bool many_columns = ctx->n > (1 << 22) || getenv("BHB200_DEBUG_FORCE_HEAVY") != nullptr;
+        if (top_wide && many_columns && ctx->bucket_enable && ctx->bucket_heavy && ctx->direct_wide) {
+            heavy_base = ct_entries;
+            for (int b = SB_B16384; b <= SB_LARGE; ++b) {
+                if (hc.sym_bin[b] <= 0) continue;
+                spec_heavy[b] = spec_wide[b] = true;
+                spec_base[b] = heavy_base;
+                ct_entries += (long long)hc.sym_bin_products[b];
+                spec_mask |= 1u << b;
+            }
+        }
         // the wide staging buffer must not crowd out C itself (at most `products` entries)
         if (spec_mask && ((size_t)ct_entries * 4 + 16 > ctx->ct_col.cap || (size_t)ct_entries * vs + 16 > ctx->ct_val.cap)) {
             // (only when the staging buffer has to grow: cudaMemGetInfo can take milliseconds)
@@ -750,10 +779,11 @@ int bhb200_spgemm(bhb200_ctx *ctx)
             const double need = ((double)ct_entries + (double)st.products) * (4.0 + vs);
             if (need > 0.9 * avail) {
                 ct_entries = 0;
-                for (int b = SB_G128; b <= SB_B8192; ++b) {
+                for (int b = SB_G128; b <= SB_LARGE; ++b) {
                     if (!((spec_mask >> b) & 1u)) continue;
                     if (spec_wide[b]) {
                         spec_mask &= ~(1u << b);
+                        spec_heavy[b] = false;
                         continue;
                     }
                     spec_base[b] = ct_entries;
@@ -786,11 +816,17 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     int cdf_shift = 0;
     if (ctx->bucket_enable && spec_mask) {
         for (int b = SB_G512; b <= SB_B8192; ++b) use_bucket |= ((spec_mask >> b) & 1u) && spec_wide[b] && spec_cap[b] >= ctx->bucket_min_cap;
+        for (int b = SB_B16384; b <= SB_LARGE; ++b) use_bucket |= ((spec_mask >> b) & 1u) && spec_heavy[b];
         if (use_bucket && (ctx->cdf_colcount.reserve(((size_t)ctx->k + 1) * 4, &ctx->dev_bytes) != cudaSuccess ||
                            ctx->cdf_hist.reserve((size_t)CDF_KNOTS * 8, &ctx->dev_bytes) != cudaSuccess ||
                            ctx->cdf_tab.reserve((size_t)(CDF_KNOTS + 1) * 4, &ctx->dev_bytes) != cudaSuccess)) {
             cudaGetLastError();
             use_bucket = false;
+            for (int b = SB_B16384; b <= SB_LARGE; ++b)
+                if (spec_heavy[b]) {   // (their staging stays allocated but unused: two-pass path)
+                    spec_heavy[b] = false;
+                    spec_mask &= ~(1u << b);
+                }
         }
         if (use_bucket)
             CU(launch_build_cdf(lc, ctx->m, ctx->k, ctx->n, ctx->nnzA, ctx->A, ctx->B, ctx->cdf_colcount.as<int>(),
@@ -803,6 +839,18 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     CU(launch_sym_esc(lc, queue + so.off[SB_ESC], hc.sym_bin[SB_ESC], ctx->n, ctx->A, ctx->B, rcnt), "symbolic ESC");
     for (int b = SB_G128; b <= SB_B32768; ++b) {
         if (hc.sym_bin[b] > 0) CU(stamp(ctx, 0, b), "event");
+        if (((spec_mask >> b) & 1u) && spec_heavy[b]) {
+            DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, heavy_base, nullptr, nullptr};
+            d.prod = prod;
+            if (ctx->dtype == BHB200_DTYPE_F64)
+                CU(launch_num_bucket_heavy_f64(lc, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, &d_ctr->heavy_cursor),
+                   "heavy bucket numeric f64");
+            else
+                CU(launch_num_bucket_heavy_f32(lc, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, &d_ctr->heavy_cursor),
+                   "heavy bucket numeric f32");
+            st.direct_rows += hc.sym_bin[b];
+            continue;
+        }
         if ((spec_mask >> b) & 1u) {
             DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, spec_base[b],
                         ctx->retry_q.as<int>() + so.off[b], &d_ctr->retry_cnt[b]};
@@ -841,7 +889,18 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         }
         CU(launch_sym_hash(lc, b, G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, rcnt), "symbolic hash");
     }
-    if (hc.sym_bin[SB_LARGE] > 0) {
+    if (hc.sym_bin[SB_LARGE] > 0 && ((spec_mask >> SB_LARGE) & 1u) && spec_heavy[SB_LARGE]) {
+        CU(stamp(ctx, 0, SB_LARGE), "event");
+        DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, heavy_base, nullptr, nullptr};
+        d.prod = prod;
+        if (ctx->dtype == BHB200_DTYPE_F64)
+            CU(launch_num_bucket_heavy_f64(lc, queue + so.off[SB_LARGE], hc.sym_bin[SB_LARGE], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, &d_ctr->heavy_cursor),
+               "heavy bucket numeric f64");
+        else
+            CU(launch_num_bucket_heavy_f32(lc, queue + so.off[SB_LARGE], hc.sym_bin[SB_LARGE], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, &d_ctr->heavy_cursor),
+               "heavy bucket numeric f32");
+        st.direct_rows += hc.sym_bin[SB_LARGE];
+    } else if (hc.sym_bin[SB_LARGE] > 0) {
         rc = reserve_large_scratch(ctx, false);
         if (rc) return rc;
         CU(stamp(ctx, 0, SB_LARGE), "event");

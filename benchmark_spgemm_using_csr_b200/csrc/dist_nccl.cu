@@ -82,7 +82,7 @@ struct DistState {
     int rank = 0, nranks = 1;
     cudaStream_t val_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_val = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-    DevBuf d_part, d_counts, d_global_rowptr;
+    DevBuf d_part, d_counts, d_global_rowptr, d_cprefix;
     Partition part{};
     Partition *h_part = nullptr;   // pinned
     long long *h_counts = nullptr;   // pinned [nranks]
@@ -121,13 +121,29 @@ int dfail(bhb200_ctx *c, int code, const char *what, const char *detail = nullpt
         if (r__ != 0) return dfail(ctx, BHB200_ERR_CUDA, what, nccl().GetErrorString ? nccl().GetErrorString(r__) : "NCCL error"); \
     } while (0)
 
-// first row i with prefix[i] >= total * r / nranks  (prefix = exclusive scan of the per-row products, n+1 entries)
-__global__ void k_partition_bounds(const int n, const int nranks, const int64_t *__restrict__ prefix,
-                                   const int *__restrict__ rowptr, Partition *__restrict__ out)
+// Cost of a row for the partition: its intermediate products, times 2.5 beyond 12288 products -- rows that
+// leave the on-chip tables (two-pass CTA tables, global-bitmap kernel) run at ~16 products/ns against ~37 for the
+// rest (profiles/r02_notes.md); R-MAT's hub rows sit at the low row indices, so equal PRODUCT shares left rank 0
+// 19 % behind at N = 2.  dist.py::row_cost is the same function.
+constexpr int COST_HEAVY_ROW = 12288;
+__global__ void k_row_cost(const int n, const int *__restrict__ prod, int *__restrict__ cost)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long p = prod[i];
+    const long long c = p > COST_HEAVY_ROW ? (p * 5) / 2 : p;
+    cost[i] = (int)(c > 0x7fffffffLL ? 0x7fffffffLL : c);
+}
+
+// first row i with cprefix[i] >= total * r / nranks  (cprefix = exclusive scan of the per-row costs, n+1 entries;
+// prefix = the same for the products, for the report)
+__global__ void k_partition_bounds(const int n, const int nranks, const int64_t *__restrict__ cprefix,
+                                   const int64_t *__restrict__ prefix, const int *__restrict__ rowptr,
+                                   Partition *__restrict__ out)
 {
     const int r = threadIdx.x;
     if (r > nranks) return;
-    const long long total = prefix[n];
+    const long long total = cprefix[n];
     long long b;
     if (r == 0) b = 0;
     else if (r == nranks) b = n;
@@ -136,14 +152,14 @@ __global__ void k_partition_bounds(const int n, const int nranks, const int64_t 
         int lo = 0, hi = n;   // first index with prefix[idx] >= target
         while (lo < hi) {
             const int mid = lo + ((hi - lo) >> 1);
-            if (prefix[mid] < target) lo = mid + 1;
+            if (cprefix[mid] < target) lo = mid + 1;
             else hi = mid;
         }
         b = lo;
     }
     out->bounds[r] = b;
     out->nnz_bounds[r] = rowptr[b];
-    if (r == 0) out->products = total;
+    if (r == 0) out->products = prefix[n];
     __syncthreads();
     if (r < nranks) out->block_products[r] = prefix[out->bounds[r + 1]] - prefix[out->bounds[r]];
 }
@@ -230,6 +246,7 @@ int bhb200_dist_finalize(bhb200_ctx *ctx)
     d->d_part.release(&ctx->dev_bytes);
     d->d_counts.release(&ctx->dev_bytes);
     d->d_global_rowptr.release(&ctx->dev_bytes);
+    d->d_cprefix.release(&ctx->dev_bytes);
     if (d->val_stream) cudaStreamDestroy(d->val_stream);
     for (cudaEvent_t e : {d->ev_ready, d->ev_val, d->ev_t0, d->ev_t1})
         if (e) cudaEventDestroy(e);
@@ -291,10 +308,17 @@ int bhb200_dist_setup_square(bhb200_ctx *ctx, int root, int dtype, int n, int64_
                                 ctx->rc.as<int>(), ctx->rlo.as<int>(), ctx->rspan.as<int>(), d_ctr),
             "row products");
         // exclusive scan of the products (the scan kernels take the per-row counts as `rc`)
-        DCU(launch_scan(lc, n, rowptr, ctx->prod.as<int>(), ctx->prod.as<int>(), ctx->rspan.as<int>(), 0u, nullptr,
+        DCU(launch_scan(lc, n, rowptr, ctx->prod.as<int>(), ctx->prod.as<int>(), nullptr, 0u, nullptr,
                         ctx->rowoff64.as<int64_t>(), ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
             "product prefix");
-        k_partition_bounds<<<1, MAX_RANKS + 1, 0, s>>>(n, d->nranks, ctx->rowoff64.as<int64_t>(), rowptr, dp);
+        // ... and of the per-row costs (rc[] and a second prefix buffer are free at this point)
+        DCU(d->d_cprefix.reserve(((size_t)n + 1) * 8, &ctx->dev_bytes), "alloc");
+        k_row_cost<<<(n + 255) / 256, 256, 0, s>>>(n, ctx->prod.as<int>(), ctx->rc.as<int>());
+        DCU(cudaGetLastError(), "row cost kernel");
+        DCU(launch_scan(lc, n, rowptr, ctx->prod.as<int>(), ctx->rc.as<int>(), nullptr, 0u, nullptr, d->d_cprefix.as<int64_t>(),
+                        ctx->rowptr32.as<int>(), ctx->blocksums.as<long long>(), d_ctr),
+            "cost prefix");
+        k_partition_bounds<<<1, MAX_RANKS + 1, 0, s>>>(n, d->nranks, d->d_cprefix.as<int64_t>(), ctx->rowoff64.as<int64_t>(), rowptr, dp);
         DCU(cudaGetLastError(), "partition kernel");
     }
     // ---- broadcast: partition record, rowptr, col on the compute stream; val on its own stream ----

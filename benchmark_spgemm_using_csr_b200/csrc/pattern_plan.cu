@@ -233,6 +233,7 @@ PatTables pattern_tables(const PatternPlan &plan, const unsigned char *dev_blob)
     t.nw = plan.nw;
     t.acc_len = plan.acc_len;
     t.fullB = t.nDB >= 64 ? ~0ull : ((1ull << t.nDB) - 1ull);
+    t.fullbits = nullptr;
     return t;
 }
 

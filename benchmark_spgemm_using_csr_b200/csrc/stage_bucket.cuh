@@ -175,4 +175,202 @@ k_num_bucket(const int *__restrict__ queue, const int count, const int *__restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// k_num_bucket_heavy: the same bucket sort for rows with MORE products than fit on chip (the rows the
+// reference sends through EM_mergepath_global, bhsparse_cuda.h:2270-2525, and round 1 sent through a global
+// column bitmap -- at n = 16.8 M columns, config 5, that kernel ran at 6 products/ns and held rank 0 at 99 ms
+// while the other ranks finished in 67, profiles/r02_notes.md).  The row is cut into slices of the
+// F-axis (F = the product-column CDF): 2^k equal slices sized for 1.5x headroom; a slice whose products
+// exceed the capacity is halved, recursively (an explicit stack, CTA-uniform control flow).  Every slice is
+// counted, scattered, sorted and emitted like a row of k_num_bucket; slices are processed in ascending F, so
+// their outputs concatenate into the sorted row.  The row's products are re-read once per slice and pass
+// (they sit in L1/L2).  A slice of a single F value that still overflows (thousands of products in one
+// column: possible only for rows of A with more entries than the capacity) is reduced column by column.
+// Direct mode: the row is staged at ct_base + [running sum of the products of the rows before it in the
+// launch, by atomic bump]; rc / ct_off as in k_num_bucket.
+// ---------------------------------------------------------------------------------------------------
+template <typename VT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
+                   const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
+                   const int *__restrict__ colB, const VT *__restrict__ valB, const ColumnCdf cdf, const int cap,
+                   const int nb, int *__restrict__ rc, long long *__restrict__ ct_off, int *__restrict__ ctcol,
+                   VT *__restrict__ ctval, const long long ct_base, unsigned long long *__restrict__ cursor,
+                   const int *__restrict__ prod)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VT *vals = reinterpret_cast<VT *>(smem_raw);                              // [cap]
+    int *keys = reinterpret_cast<int *>(smem_raw + (size_t)cap * sizeof(VT));   // [cap]
+    int *cnt = keys + cap;                                                    // [nb]
+    int *ocnt = cnt + nb;                                                     // [nb + 1]
+    int *scratch = ocnt + nb + 1;                                             // [34]
+    __shared__ unsigned s_stack_lo[40];
+    __shared__ int s_stack_lg[40];
+    __shared__ long long s_row_base;
+    __shared__ int s_min;
+    __shared__ double s_sum;
+    const int lane = threadIdx.x & 31;
+
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int row = queue[q];
+        const int p = prod[row];
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        if (threadIdx.x == 0) s_row_base = ct_base + (long long)atomicAdd(cursor, (unsigned long long)p);
+        // first cut: 2^lg0 slices with 1.5x headroom
+        int lg0 = 0;
+        while (lg0 < 20 && ((long long)cap << lg0) * 2 < (long long)p * 3) ++lg0;
+        __syncthreads();
+        const long long o = s_row_base;
+        int written = 0;   // CTA-uniform
+        for (unsigned first = 0; first < (1u << lg0); ++first) {
+            int sp = 0;   // stack pointer (CTA-uniform: every thread tracks it)
+            if (threadIdx.x == 0) {
+                s_stack_lo[0] = lg0 ? first << (32 - lg0) : 0u;
+                s_stack_lg[0] = 32 - lg0;
+            }
+            sp = 1;
+            while (sp > 0) {
+                __syncthreads();
+                const unsigned lo = s_stack_lo[sp - 1];
+                const int lgw = s_stack_lg[sp - 1];   // the slice is [lo, lo + 2^lgw) on the F axis (lgw = 32: everything)
+                --sp;
+                // ---- count ----
+                for (int i = threadIdx.x; i < nb; i += THREADS) cnt[i] = 0;
+                if (threadIdx.x == 0) scratch[33] = 0;
+                __syncthreads();
+                for (int j = a0 + take_next(&scratch[33], lane); j < a1; j = a0 + take_next(&scratch[33], lane)) {
+                    const int k = colA[j];
+                    const int bs = rowptrB[k], be = rowptrB[k + 1];
+                    for (int e = bs + lane; e < be; e += 32) {
+                        const unsigned rel = cdf_eval(cdf, colB[e]) - lo;
+                        if (lgw == 32 || (rel >> lgw) == 0u) atomicAdd(&cnt[__umulhi(lgw == 32 ? rel : rel << (32 - lgw), (unsigned)nb)], 1);
+                    }
+                }
+                __syncthreads();
+                const int total = cta_exclusive_scan<THREADS>(cnt, nb, scratch);
+                if (total == 0) continue;
+                if (total > cap) {
+                    if (lgw > 0) {   // halve the slice: lower half on top of the stack
+                        if (threadIdx.x == 0) {
+                            s_stack_lo[sp] = lo + (1u << (lgw - 1));
+                            s_stack_lg[sp] = lgw - 1;
+                            s_stack_lo[sp + 1] = lo;
+                            s_stack_lg[sp + 1] = lgw - 1;
+                        }
+                        sp += 2;
+                        continue;
+                    }
+                    // one F value with more products than the capacity: reduce it column by column (ascending)
+                    int last = -1;
+                    while (true) {
+                        if (threadIdx.x == 0) {
+                            s_min = 0x7fffffff;
+                            s_sum = 0.0;
+                        }
+                        __syncthreads();
+                        int mymin = 0x7fffffff;
+                        for (int j = a0 + (int)(threadIdx.x >> 5); j < a1; j += THREADS / 32) {
+                            const int k = colA[j];
+                            for (int e = rowptrB[k] + lane; e < rowptrB[k + 1]; e += 32) {
+                                const int c = colB[e];
+                                if (c > last && cdf_eval(cdf, c) == lo) mymin = min(mymin, c);
+                            }
+                        }
+                        mymin = min(mymin, __shfl_xor_sync(FULL, mymin, 16));
+                        mymin = min(mymin, __shfl_xor_sync(FULL, mymin, 8));
+                        mymin = min(mymin, __shfl_xor_sync(FULL, mymin, 4));
+                        mymin = min(mymin, __shfl_xor_sync(FULL, mymin, 2));
+                        mymin = min(mymin, __shfl_xor_sync(FULL, mymin, 1));
+                        if (lane == 0) atomicMin(&s_min, mymin);
+                        __syncthreads();
+                        const int cmin = s_min;
+                        if (cmin == 0x7fffffff) break;
+                        double part = 0.0;
+                        for (int j = a0 + (int)(threadIdx.x >> 5); j < a1; j += THREADS / 32) {
+                            const int k = colA[j];
+                            const VT av = valA[j];
+                            for (int e = rowptrB[k] + lane; e < rowptrB[k + 1]; e += 32)
+                                if (colB[e] == cmin) part += (double)(av * valB[e]);
+                        }
+                        part = warp_sum(part);
+                        if (lane == 0 && part != 0.0) atomicAdd(&s_sum, part);
+                        __syncthreads();
+                        if (threadIdx.x == 0) {
+                            ctcol[o + written] = cmin;
+                            ctval[o + written] = (VT)s_sum;
+                        }
+                        ++written;
+                        last = cmin;
+                        __syncthreads();
+                    }
+                    continue;
+                }
+                // ---- scatter ----
+                if (threadIdx.x == 0) scratch[33] = 0;
+                __syncthreads();
+                for (int j = a0 + take_next(&scratch[33], lane); j < a1; j = a0 + take_next(&scratch[33], lane)) {
+                    const int k = colA[j];
+                    const VT av = valA[j];
+                    const int bs = rowptrB[k], be = rowptrB[k + 1];
+                    for (int e = bs + lane; e < be; e += 32) {
+                        const int c = colB[e];
+                        const unsigned rel = cdf_eval(cdf, c) - lo;
+                        if (lgw == 32 || (rel >> lgw) == 0u) {
+                            const int slot = atomicAdd(&cnt[__umulhi(lgw == 32 ? rel : rel << (32 - lgw), (unsigned)nb)], 1);
+                            keys[slot] = c;
+                            vals[slot] = av * valB[e];
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- per bucket: insertion sort, merge equal columns ----
+                for (int b = threadIdx.x; b < nb; b += THREADS) {
+                    const int s = b ? cnt[b - 1] : 0, e = cnt[b];
+                    for (int i = s + 1; i < e; ++i) {
+                        const int kc = keys[i];
+                        const VT kv = vals[i];
+                        int j = i - 1;
+                        while (j >= s && keys[j] > kc) {
+                            keys[j + 1] = keys[j];
+                            vals[j + 1] = vals[j];
+                            --j;
+                        }
+                        keys[j + 1] = kc;
+                        vals[j + 1] = kv;
+                    }
+                    int w = s;
+                    for (int i = s; i < e; ++i) {
+                        if (i > s && keys[i] == keys[w - 1]) {
+                            vals[w - 1] += vals[i];
+                        } else {
+                            keys[w] = keys[i];
+                            vals[w] = vals[i];
+                            ++w;
+                        }
+                    }
+                    ocnt[b] = w - s;
+                }
+                if (threadIdx.x == 0) ocnt[nb] = 0;
+                __syncthreads();
+                const int out = cta_exclusive_scan<THREADS>(ocnt, nb + 1, scratch);
+                for (int b = threadIdx.x; b < nb; b += THREADS) {
+                    const int s = b ? cnt[b - 1] : 0;
+                    const int o0 = ocnt[b], n = ocnt[b + 1] - o0;
+                    for (int i = 0; i < n; ++i) {
+                        ctcol[o + written + o0 + i] = keys[s + i];
+                        ctval[o + written + o0 + i] = vals[s + i];
+                    }
+                }
+                written += out;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            rc[row] = written;
+            ct_off[row] = o;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace bhb

@@ -68,9 +68,13 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
                                                       Counters *__restrict__ ctr)
 {
     __shared__ int s_hist[MAX_BINS];
+    __shared__ unsigned long long s_hprod[MAX_BINS];
     __shared__ unsigned long long s_total;
     __shared__ int s_max, s_ovf;
-    if (threadIdx.x < MAX_BINS) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x < MAX_BINS) {
+        s_hist[threadIdx.x] = 0;
+        s_hprod[threadIdx.x] = 0ull;
+    }
     if (threadIdx.x == 0) {
         s_total = 0ull;
         s_max = 0;
@@ -86,6 +90,7 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
     unsigned long long my_total = 0ull;
     int my_max = 0;
     int h_bin = -1, h_cnt = 0;   // run-length aggregation of the histogram updates (rows of a thread mostly share a bin)
+    unsigned long long h_prod = 0ull;
 
     // warp-uniform loops (maxima over the groups of the warp): sub-warp groups with their
     // own trip counts would not reconverge
@@ -136,16 +141,24 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
             if (p <= 1) rc[row] = p;
             const int sbin = sym_bin_of(p, span);
             if (sbin != h_bin) {
-                if (h_cnt) atomicAdd(&s_hist[h_bin], h_cnt);
+                if (h_cnt) {
+                    atomicAdd(&s_hist[h_bin], h_cnt);
+                    atomicAdd(&s_hprod[h_bin], h_prod);
+                }
                 h_bin = sbin;
                 h_cnt = 0;
+                h_prod = 0ull;
             }
             ++h_cnt;
+            h_prod += (unsigned long long)p;
             my_total += (unsigned long long)s;
             my_max = max(my_max, p);
         }
     }
-    if (h_cnt) atomicAdd(&s_hist[h_bin], h_cnt);
+    if (h_cnt) {
+        atomicAdd(&s_hist[h_bin], h_cnt);
+        atomicAdd(&s_hprod[h_bin], h_prod);
+    }
     // block reduction of totals
     my_total = warp_sum(my_total);
 #pragma unroll
@@ -155,7 +168,10 @@ __global__ void __launch_bounds__(256) k_row_products(const int m, const int *__
         atomicMax(&s_max, my_max);
     }
     __syncthreads();
-    if (threadIdx.x < MAX_BINS && s_hist[threadIdx.x]) atomicAdd(&ctr->sym_bin[threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x < MAX_BINS && s_hist[threadIdx.x]) {
+        atomicAdd(&ctr->sym_bin[threadIdx.x], s_hist[threadIdx.x]);
+        atomicAdd(&ctr->sym_bin_products[threadIdx.x], s_hprod[threadIdx.x]);
+    }
     if (threadIdx.x == 0) {
         if (s_total) atomicAdd(&ctr->products, s_total);
         atomicMax(&ctr->max_row_products, s_max);

@@ -826,6 +826,28 @@ static cudaError_t launch_num_bucket_t(const LaunchCtx &lc, int cap, const int *
 }
 
 template <typename VT>
+static cudaError_t launch_num_bucket_heavy_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                             ColumnCdf cdf, unsigned long long *cursor)
+{
+    if (count <= 0) return cudaSuccess;
+    constexpr int THREADS = 1024;
+    constexpr int cap = sizeof(VT) == 8 ? 12288 : 16384;   // entries of a slice held on chip
+    constexpr int nb = cap / 8;
+    const size_t smem = (size_t)cap * (sizeof(VT) + 4) + (size_t)(2 * nb + 1 + 34) * 4;
+    auto kern = k_num_bucket_heavy<VT, THREADS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long blocks = count;
+    const long long lim = (long long)lc.sm_count * resident_blocks(kern, THREADS, smem);
+    if (blocks > lim) blocks = lim;
+    ++*lc.launches;
+    kern<<<(int)blocks, THREADS, smem, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
+                                                    (const VT *)B.val, cdf, cap, nb, d.rc, d.ct_off, d.ctcol, (VT *)d.ctval,
+                                                    d.ct_base, cursor, d.prod);
+    return cudaGetLastError();
+}
+
+template <typename VT>
 static cudaError_t launch_copy_ct_t(const LaunchCtx &lc, const int *queue, int count, const int64_t *rowoff,
                                     const long long *ct_off, const int *ctcol, const VT *ctval, int *colC, VT *valC,
                                     double avg_row)

@@ -38,4 +38,10 @@ cudaError_t launch_num_bucket_f32(const LaunchCtx &lc, int cap, const int *queue
     return launch_num_bucket_t<float>(lc, cap, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift});
 }
 
+cudaError_t launch_num_bucket_heavy_f32(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                        const unsigned *cdf, int cdf_shift, unsigned long long *cursor)
+{
+    return launch_num_bucket_heavy_t<float>(lc, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift}, cursor);
+}
+
 }  // namespace bhb

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) k_pat_codes(const int rows, const int nco
                                                    const int *__restrict__ col, const int *__restrict__ offs,
                                                    const int noffs, const int span, unsigned char *__restrict__ code,
                                                    unsigned long long *__restrict__ rowmask, int *__restrict__ bad,
-                                                   int *__restrict__ miss)
+                                                   int *__restrict__ miss, int *__restrict__ col_range_out,
+                                                   const int *__restrict__ row_range)
 {
     __shared__ int s_offs[PAT_MAX_OFFS];
     extern __shared__ unsigned char s_tab[];
@@ -140,12 +141,22 @@ __global__ void __launch_bounds__(256) k_pat_codes(const int rows, const int nco
     }
     const int gl = threadIdx.x & 7;
     const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
-    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < rows; r += stride) {
+    // row_range (B in a multi-GPU row block): only the rows of B that the block of A references are coded
+    // and checked -- {largest column of A, INT_MAX - smallest column of A} as written by the pass over A
+    long long r_first = 0, r_end = rows;
+    if (row_range) {
+        r_first = 0x7fffffffLL - (long long)row_range[1];
+        r_end = min((long long)rows, (long long)row_range[0] + 1);
+    }
+    int cmax = 0, cnegmax = 0;
+    for (long long r = r_first + (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3); r < r_end; r += stride) {
         const int s = rowptr[r], e = rowptr[r + 1];
         unsigned long long mask = 0ull;
         bool wrong = e < s, unknown = false;
         for (int p = s + gl; p < e; p += 8) {
             const int c = col[p];
+            cmax = max(cmax, c);
+            cnegmax = max(cnegmax, 0x7fffffff - c);
             // the operand preconditions (see k_b_row_ranges): columns inside the matrix; for B
             // (rowmask != nullptr) strictly ascending along the row
             wrong |= (unsigned)c >= (unsigned)ncols;
@@ -179,6 +190,17 @@ __global__ void __launch_bounds__(256) k_pat_codes(const int rows, const int nco
             if (gl == 0) rowmask[r] = mask;
         }
     }
+    if (col_range_out) {   // column range of the matrix (a pass over A): which rows of B matter
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            cmax = max(cmax, __shfl_xor_sync(FULL, cmax, d));
+            cnegmax = max(cnegmax, __shfl_xor_sync(FULL, cnegmax, d));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(&col_range_out[0], cmax);
+            atomicMax(&col_range_out[1], cnegmax);
+        }
+    }
 }
 
 // one bit per row of B: the row holds every offset of DB (then its image under any A offset is the
@@ -194,7 +216,7 @@ __global__ void __launch_bounds__(256) k_pat_fullbits(const int rows, const unsi
 
 cudaError_t launch_pat_codes(const LaunchCtx &lc, int rows, int ncols, const int *rowptr, const int *col, const int *offs,
                              int noffs, long long span, unsigned char *code, unsigned long long *rowmask, int *bad, int *miss,
-                             unsigned long long full, unsigned *fullbits)
+                             unsigned long long full, unsigned *fullbits, int *col_range_out, const int *row_range)
 {
     if (rows <= 0) return cudaSuccess;
     long long blocks = ((long long)rows * 8 + 255) / 256;
@@ -203,9 +225,11 @@ cudaError_t launch_pat_codes(const LaunchCtx &lc, int rows, int ncols, const int
     ++*lc.launches;
     if (span > 0 && span <= PAT_DIRECT_SPAN) {
         const size_t smem = ((size_t)span + 15) & ~(size_t)15;
-        k_pat_codes<true><<<(int)blocks, 256, smem, lc.stream>>>(rows, ncols, rowptr, col, offs, noffs, (int)span, code, rowmask, bad, miss);
+        k_pat_codes<true><<<(int)blocks, 256, smem, lc.stream>>>(rows, ncols, rowptr, col, offs, noffs, (int)span, code, rowmask, bad,
+                                                                  miss, col_range_out, row_range);
     } else {
-        k_pat_codes<false><<<(int)blocks, 256, 0, lc.stream>>>(rows, ncols, rowptr, col, offs, noffs, 0, code, rowmask, bad, miss);
+        k_pat_codes<false><<<(int)blocks, 256, 0, lc.stream>>>(rows, ncols, rowptr, col, offs, noffs, 0, code, rowmask, bad, miss,
+                                                                col_range_out, row_range);
     }
     if (rowmask && fullbits) {
         ++*lc.launches;
@@ -614,7 +638,10 @@ k_pat_numeric(const int m, const int *__restrict__ rowptrA, const int *__restric
                 const int k = colA[a0 + j];
                 const int bs = rowptrB[k];
                 const int len = rowptrB[k + 1] - bs;
-                rec[gl] = PatRec<VT>::pack(bs, len | (((int)ta[a0 + j] * nDB) << 16), valA[a0 + j]);   // (ja * nDB <= 63 * 64)
+                // bit 15: the B row holds every offset of DB, so its l-th entry has code l and the code bytes
+                // need not be read (all interior rows of a stencil)
+                const int full = (t.fullbits && ((__ldg(t.fullbits + (k >> 5)) >> (k & 31)) & 1u)) ? 0x8000 : 0;
+                rec[gl] = PatRec<VT>::pack(bs, len | full | (((int)ta[a0 + j] * nDB) << 16), valA[a0 + j]);   // (ja * nDB <= 63 * 64)
             } else {
                 rec[gl] = make_int4(0, 0, 0, 0);   // length 0: nothing to do for this slot
             }
@@ -631,17 +658,18 @@ k_pat_numeric(const int m, const int *__restrict__ rowptrA, const int *__restric
 #define PAT_LOAD(R, JB, BV, ON, TT)                                      \
     do {                                                                  \
         R = lds_v4(rec_s + (unsigned)(TT) * 16u);                        \
-        ON = gl < (R.y & 0xffff);                                         \
+        ON = gl < (R.y & 0x7fff);                                         \
         /* lanes past the end re-read the row's first element (same cache line, no branch); empty row: element 0 */ \
-        const int idx__ = ON ? R.x + gl : ((R.y & 0xffff) ? R.x : 0);    \
-        JB = tb[idx__];                                                   \
+        const int idx__ = ON ? R.x + gl : ((R.y & 0x7fff) ? R.x : 0);    \
+        if (G == 32 && !LONGB && (R.y & 0x8000)) JB = gl; /* full row (warp-uniform test): code = lane */ \
+        else JB = tb[idx__];                                              \
         BV = valB[idx__];                                                 \
     } while (0)
 #define PAT_ACCUM(R, JB, BV, ON)                                                          \
     do {                                                                                   \
         pat_accum_if(ON, mphys_s + (unsigned)(R.y >> 16) + (unsigned)(JB), acc_s, PatRec<VT>::val(R), BV); \
         if constexpr (LONGB) {                                                             \
-            const int len__ = R.y & 0xffff;                                                \
+            const int len__ = R.y & 0x7fff;                                                \
             _Pragma("unroll 1") for (int off = G + gl; off < len__; off += G) {            \
                 const int q__ = lds_u8(mphys_s + (unsigned)(R.y >> 16) + (unsigned)tb[R.x + off]); \
                 const unsigned b__ = acc_s + (unsigned)q__ * (unsigned)sizeof(VT);         \

@@ -46,6 +46,7 @@ struct PatTables {
     const int *offsB;             // [nDB] sorted
     int nDA, nDB, nD, nw, acc_len;
     unsigned long long fullB;     // mask with nDB bits set
+    const unsigned *fullbits;     // one bit per row of B: the row holds every offset of DB (set by the caller; may be null)
 };
 
 // launchers (stage_pattern.cu)
@@ -54,9 +55,11 @@ cudaError_t launch_offset_set(const LaunchCtx &lc, int rows, const int *rowptr, 
 // span = largest - smallest offset + 1 (a small span selects the direct-table kernel)
 // miss: set to 1 if an entry's offset is not in `offs` (a cached plan no longer describes the matrix)
 // fullbits (with rowmask): one bit per row, "holds every offset" (rowmask == full)
+// col_range_out: {max column, INT_MAX - min column} of the matrix by atomicMax (zero-initialised by the caller)
+// row_range: such a pair in device memory; only rows inside it are coded and checked (nullptr: all rows)
 cudaError_t launch_pat_codes(const LaunchCtx &lc, int rows, int ncols, const int *rowptr, const int *col, const int *offs,
                              int noffs, long long span, unsigned char *code, unsigned long long *rowmask, int *bad, int *miss,
-                             unsigned long long full, unsigned *fullbits);
+                             unsigned long long full, unsigned *fullbits, int *col_range_out, const int *row_range);
 cudaError_t launch_pat_symbolic(const LaunchCtx &lc, int m, Csr A, const unsigned char *ta, const unsigned long long *maskB,
                                 PatTables t, unsigned *outmask, int *rc, int *prod, Counters *ctr, int k, double avg_row,
                                 const unsigned *fullbits);

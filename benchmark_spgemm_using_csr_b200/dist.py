@@ -42,6 +42,17 @@ def row_products_host(A: CSR, B_rowptr: np.ndarray) -> np.ndarray:
     return csum[A.rowptr[1:].astype(np.int64)] - csum[A.rowptr[:-1].astype(np.int64)]
 
 
+COST_HEAVY_ROW = 12288
+
+
+def row_cost(row_products: np.ndarray) -> np.ndarray:
+    """Cost of a row for the partition (csrc/dist_nccl.cu::k_row_cost is the same function): its
+    intermediate products, times 2.5 beyond 12288 products -- rows that leave the on-chip tables run at
+    ~16 products/ns against ~37 for the rest, and R-MAT's hub rows all sit in the first block."""
+    p = row_products.astype(np.int64)
+    return np.minimum(np.where(p > COST_HEAVY_ROW, (p * 5) // 2, p), np.int64(0x7FFFFFFF))
+
+
 def partition_rows_by_products(row_products: np.ndarray, world: int) -> np.ndarray:
     """Boundaries b[0..world] with b[0]=0, b[world]=m such that every block holds
     about the same number of intermediate products (a row is never split)."""
@@ -176,7 +187,7 @@ class RowBlockSpGEMM:
         dev = self.device
         if self.rank == root:
             prods = row_products_host(A, B.rowptr)
-            bounds = partition_rows_by_products(prods, self.world)
+            bounds = partition_rows_by_products(row_cost(prods), self.world)
             meta = dict(m=A.rows, k=A.cols, n=B.cols, nnzA=A.nnz, nnzB=B.nnz, dtype=str(A.val.dtype),
                         bounds=bounds.tolist(), nnz_bounds=[int(A.rowptr[b]) for b in bounds],
                         products=int(prods.sum()))
@@ -235,15 +246,19 @@ class RowBlockSpGEMM:
             prefix = torch.zeros(n + 1, dtype=torch.int64, device=dev)
             torch.cumsum(prods, 0, out=prefix[1:])
             total = int(prefix[-1].item())
-            targets = torch.tensor([(total * r) // self.world for r in range(1, self.world)], dtype=torch.int64, device=dev)
-            inner = torch.searchsorted(prefix, targets, right=False).clamp(max=n).cpu().numpy() if self.world > 1 else []
+            cost = torch.where(prods > COST_HEAVY_ROW, (prods * 5) // 2, prods).clamp(max=0x7FFFFFFF)      # row_cost()
+            cprefix = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(cost, 0, out=cprefix[1:])
+            ctotal = int(cprefix[-1].item())
+            targets = torch.tensor([(ctotal * r) // self.world for r in range(1, self.world)], dtype=torch.int64, device=dev)
+            inner = torch.searchsorted(cprefix, targets, right=False).clamp(max=n).cpu().numpy() if self.world > 1 else []
             bounds = np.maximum.accumulate(np.concatenate([[0], np.asarray(inner, dtype=np.int64), [n]]).astype(np.int64))
             nnz_bounds = [int(x) for x in Brp[torch.from_numpy(bounds).to(dev)].cpu().numpy()]
             block_products = [int((prefix[int(bounds[r + 1])] - prefix[int(bounds[r])]).item()) for r in range(self.world)]
             meta = dict(m=n, k=n, n=n, nnzA=int(Bc.numel()), nnzB=int(Bc.numel()), dtype=str(Bv.dtype).replace("torch.", ""),
                         bounds=bounds.tolist(), nnz_bounds=nnz_bounds, products=total, block_products=block_products,
                         max_row_products=int(prods.max().item()))
-            del lenB, csum, rp64, prods, prefix
+            del lenB, csum, rp64, prods, prefix, cost, cprefix
         else:
             meta = None
         if self.world > 1:

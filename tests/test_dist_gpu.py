@@ -116,11 +116,11 @@ def _cabi_run(rank, world, dev, out_dir):
 
 def _cabi_check(out_dir, world):
     import oracle
-    from benchmark_spgemm_using_csr_b200.dist import partition_rows_by_products, row_products_host
+    from benchmark_spgemm_using_csr_b200.dist import partition_rows_by_products, row_cost, row_products_host
     for name, A in _square_cases().items():
         wrp, wcol, wval = oracle.spgemm(A.rows, A.cols, A.cols, A.rowptr, A.col, A.val, A.rowptr, A.col, A.val)
         prods = row_products_host(A, A.rowptr)
-        bounds = partition_rows_by_products(prods, world)     # the device partition must equal the host one
+        bounds = partition_rows_by_products(row_cost(prods), world)     # the device partition must equal the host one
         for r in range(world):
             g = np.load(os.path.join(out_dir, f"cabi_{name}_r{r}.npz"))
             r0, r1, off = int(g["r0"]), int(g["r1"]), int(g["off"])

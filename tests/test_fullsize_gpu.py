@@ -16,7 +16,7 @@ import pytest
 
 import oracle
 from benchmark_spgemm_using_csr_b200 import (BHSPARSE_CUDA, NUM_PLATFORMS, bhsparse, capi, generators as gen, spgemm)
-from benchmark_spgemm_using_csr_b200.dist import partition_rows_by_products, row_products_host
+from benchmark_spgemm_using_csr_b200.dist import partition_rows_by_products, row_cost, row_products_host
 from conftest import assert_csr_equal
 
 pytestmark = pytest.mark.gpu
@@ -115,9 +115,10 @@ def test_config5_partition_rmat21(rmat21, world):
     """R-MAT scale 21 (config 5's generator, three scales down) through the N-way row-block scheme."""
     A, (wrp, wcol, wval) = rmat21
     prods = row_products_host(A, A.rowptr)
-    bounds = partition_rows_by_products(prods, world)
-    share = [int(prods[bounds[r]:bounds[r + 1]].sum()) for r in range(world)]
-    assert max(share) <= 1.05 * (sum(share) / world) + prods.max()       # blocks balanced on products
+    cost = row_cost(prods)
+    bounds = partition_rows_by_products(cost, world)
+    share = [int(cost[bounds[r]:bounds[r + 1]].sum()) for r in range(world)]
+    assert max(share) <= 1.05 * (sum(share) / world) + cost.max()        # blocks balanced on the cost of their products
     off = 0
     for r in range(world):
         r0, r1 = int(bounds[r]), int(bounds[r + 1])

@@ -412,3 +412,32 @@ def test_host_memory_spill(dt, monkeypatch):
     rp, col, val, st = spgemm(L, _identity(120000, dt), return_stats=True)
     assert st["spill_bytes"] > 0 and st["num_bin_rows"][12] > 0
     assert_csr_equal((rp, col, val), _oracle(L, _identity(120000, dt)), what="spill large rows")
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_heavy_rows_sliced_bucket_sort(dt, monkeypatch):
+    """Rows with more products than the on-chip tables hold (k_num_bucket_heavy): forced here, since small
+    matrices never pass the sampling that selects it.  Cases: rows that do not compress at all, rows with
+    heavy duplication, a row just over the smallest heavy bin, and the pathological one -- tens of thousands
+    of products in ONE column, which no slicing of the column axis can split (reduced column by column)."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("general path only")
+    monkeypatch.setenv("BHB200_DEBUG_FORCE_HEAVY", "1")
+    n = 400000
+    # (a) no compression: B = identity, rows of A with 13000 .. 60000 distinct columns
+    A = gen.random_csr(6, n, np.array([13000, 60000, 5, 24577, 0, 30000]), seed=21, dtype=dt)
+    st = _check(A, _identity(n, dt), f"heavy identity {dt.__name__}")
+    assert st["direct_rows"] >= 4
+    # (b) duplicates: B rows of 40 entries over 3000 columns -> every output column hit ~50 times
+    k = 5000
+    A = gen.random_csr(4, k, np.array([4000, 1500, 700, 2]), seed=22, dtype=dt)
+    B = gen.random_csr(k, 3000, 40, seed=23, value_seed=24, dtype=dt)
+    _check(A, B, f"heavy duplicates {dt.__name__}")
+    # (c) one column carries 30000 products: every B row holds column 7 (+ three random ones)
+    k = 30000
+    rng = np.random.default_rng(5)
+    others = 8 + np.sort(rng.integers(0, (n - 8) // 3, size=(k, 3)), axis=1) * 3 + np.arange(3)     # three distinct columns > 7
+    cols = np.concatenate([np.full((k, 1), 7), others], axis=1)
+    B = CSR(k, n, (np.arange(k + 1) * 4).astype(np.int32), cols.reshape(-1).astype(np.int32), gen.int_values(4 * k, 9, dt))
+    A = gen.random_csr(3, k, np.array([k, 20000, 9]), seed=25, dtype=dt)
+    _check(A, B, f"heavy single column {dt.__name__}")
