@@ -832,7 +832,9 @@ static cudaError_t launch_num_bucket_heavy_t(const LaunchCtx &lc, const int *que
     if (count <= 0) return cudaSuccess;
     constexpr int THREADS = 1024;
     constexpr int cap = sizeof(VT) == 8 ? 12288 : 16384;   // entries of a slice held on chip
-    constexpr int nb = cap / 8;
+    // buckets per slice: capacity / BHB200_HEAVY_DIV (default 2; measured on R-MAT 24 rank 0: /2 70.3, /4 72.5, /8 72.8 ms)
+    static const int div = [] { const char *e = getenv("BHB200_HEAVY_DIV"); const int v = e ? atoi(e) : 2; return (v == 2 || v == 4 || v == 8) ? v : 2; }();
+    const int nb = cap / div;
     const size_t smem = (size_t)cap * (sizeof(VT) + 4) + (size_t)(2 * nb + 1 + 34) * 4;
     auto kern = k_num_bucket_heavy<VT, THREADS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -638,10 +638,7 @@ k_pat_numeric(const int m, const int *__restrict__ rowptrA, const int *__restric
                 const int k = colA[a0 + j];
                 const int bs = rowptrB[k];
                 const int len = rowptrB[k + 1] - bs;
-                // bit 15: the B row holds every offset of DB, so its l-th entry has code l and the code bytes
-                // need not be read (all interior rows of a stencil)
-                const int full = (t.fullbits && ((__ldg(t.fullbits + (k >> 5)) >> (k & 31)) & 1u)) ? 0x8000 : 0;
-                rec[gl] = PatRec<VT>::pack(bs, len | full | (((int)ta[a0 + j] * nDB) << 16), valA[a0 + j]);   // (ja * nDB <= 63 * 64)
+                rec[gl] = PatRec<VT>::pack(bs, len | (((int)ta[a0 + j] * nDB) << 16), valA[a0 + j]);   // (ja * nDB <= 63 * 64)
             } else {
                 rec[gl] = make_int4(0, 0, 0, 0);   // length 0: nothing to do for this slot
             }
@@ -661,8 +658,8 @@ k_pat_numeric(const int m, const int *__restrict__ rowptrA, const int *__restric
         ON = gl < (R.y & 0x7fff);                                         \
         /* lanes past the end re-read the row's first element (same cache line, no branch); empty row: element 0 */ \
         const int idx__ = ON ? R.x + gl : ((R.y & 0x7fff) ? R.x : 0);    \
-        if (G == 32 && !LONGB && (R.y & 0x8000)) JB = gl; /* full row (warp-uniform test): code = lane */ \
-        else JB = tb[idx__];                                              \
+        JB = tb[idx__]; /* (measured and dropped: skipping this load for B rows that hold every offset -- */ \
+                        /*  code = lane -- the uniform branch cost more than the load: 3.8 -> 4.3 ms)   */ \
         BV = valB[idx__];                                                 \
     } while (0)
 #define PAT_ACCUM(R, JB, BV, ON)                                                          \
