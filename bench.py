@@ -686,14 +686,13 @@ def main():
                # second stated baseline: the reference's own CUDA implementation (oracle/_ref) on this GPU
                "reference_gpu": reference_gpu_time(A, B, P_total)}
 
-    cfg = config_dict(desc, meta["m"], meta["nnzA"], P_total, t["nnz_total"], world)
-    cfg["nnzC_rank0"] = t["nnz_local"]
+    cfg = config_dict(desc, meta["m"], meta["nnzA"], P_total, t["nnz_total"], world)     # same keys and values as the reference arm's
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "wall_ms_per_step": t["wall_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic", "config": cfg,
         "roofline": roofline, "roofline_step": roof_step, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
-        "gpu_launches": t["launches"], "clocks": t["clocks"],
+        "gpu_launches": t["launches"], "clocks": t["clocks"], "nnzC_rank0": t["nnz_local"],
         "rank_ms": {"max": ms, "min": t["ms_min_rank"]},
         "stages_ms": {"count_bin": st["ms_count"], "symbolic": st["ms_symbolic"], "scan_alloc": st["ms_scan"],
                       "numeric": st["ms_numeric"], "total": st["ms_total"]},
