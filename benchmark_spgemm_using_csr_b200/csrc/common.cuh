@@ -202,6 +202,13 @@ __device__ __forceinline__ int take_next(int *counter, int lane)
     return __shfl_sync(FULL, j, 0);
 }
 
+__device__ __forceinline__ int take_next_n(int *counter, int lane, int n)
+{
+    int j = 0;
+    if (lane == 0) j = atomicAdd(counter, n);
+    return __shfl_sync(FULL, j, 0);
+}
+
 // B rows of one A row, for the CTA-per-row kernels that accumulate in GLOBAL memory (large rows).
 // Warps take B rows from a shared counter; a B row longer than LONG_B would keep one warp busy for
 // hundreds of dependent global-memory round trips (R-MAT hub columns: thousands of elements), so

@@ -176,6 +176,257 @@ k_num_bucket(const int *__restrict__ queue, const int count, const int *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_num_bucket3 (round 2, second pass): the same sort with ONE pass over the B rows and no per-bucket loops
+// by single threads.  ncu of k_num_bucket (profiles/r02_ncu_bucket_v1.txt): L1TEX 74 % -- 7.5 sectors per
+// global load request, because every product looks the CDF table up twice per pass through L1 (32 lanes,
+// ~25 different sectors) -- and 45 % of its instructions run at 3-4 active lanes (a thread per bucket).
+//   * the CDF table sits in shared memory (all 4096 knots, or every fourth for the small capacities);
+//   * the row's A entries are staged a chunk at a time as {B row start, length, first product index}: the
+//     colA -> rowptrB -> colB chain of dependent loads is paid once per chunk by all threads in parallel,
+//     not once per B row by one warp;
+//   * pass 1 (the only one over B): product t = (column, a*b) is staged at its running index, its bucket's
+//     counter gives (bucket, arrival) -- one shared-memory atomic per product instead of two;
+//   * after the scan the columns are copied into bucket order (dense loop), every PRODUCT ranks itself
+//     inside its bucket (1-2 members on average: nb = cap/2 buckets for rows of cap/2 .. cap products) and
+//     writes its column and its index at the rank: the row is sorted;
+//   * emit walks the sorted row with whole warps: heads of equal-column runs sum their run, a ballot scan
+//     compacts, stores are coalesced.
+// Members of buckets longer than B3_BIG (hub columns of skewed matrices, rows that do compress) are ranked
+// by their whole warp, one member at a time, so one long bucket does not stretch every lane's loop.
+// ---------------------------------------------------------------------------------------------------
+constexpr int B3_LONG = 512;      // B rows longer than this are strided over by the whole CTA
+constexpr int B3_LONG_CAP = 64;
+constexpr int B3_BIG = 12;        // bucket sizes above this: warp-cooperative ranking
+constexpr int B3_U = 2;           // B rows a warp takes (and loads) at a time
+constexpr int B3_SCRATCH = 80;    // ints: [0,34) scan, 34 next, 35 nlong, 36 cursor, [40,72) heads per warp
+
+template <int THREADS>
+__host__ __device__ constexpr int b3_chunk()
+{
+    return THREADS < 512 ? THREADS : (THREADS == 768 ? 256 : 512);   // (768 threads: the variant sized for two CTAs per SM)
+}
+
+template <typename VT, int THREADS>
+inline size_t b3_smem_bytes(const int cap, const int nb, const int knots)
+{
+    return (size_t)b3_chunk<THREADS>() * (16 + sizeof(VT)) + (size_t)cap * (sizeof(VT) + 12) + (size_t)(nb + 1) * 4 +
+           (size_t)(knots + 1) * 4 + (size_t)(B3_SCRATCH + B3_LONG_CAP) * 4 + (size_t)cap * 2;
+}
+
+template <typename VT, int THREADS, int KB>
+__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 1536 / THREADS)   // 1536 threads per SM, or one full-size CTA
+k_num_bucket3(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA, const int *__restrict__ colA,
+              const VT *__restrict__ valA, const int *__restrict__ rowptrB, const int *__restrict__ colB,
+              const VT *__restrict__ valB, const ColumnCdf cdf, const int cap, const int nb, int *__restrict__ rc,
+              long long *__restrict__ ct_off, int *__restrict__ ctcol, VT *__restrict__ ctval, const long long ct_base,
+              const int *__restrict__ prod, const int p_lo, const int p_hi, const int ct_stride)
+{
+    constexpr int K = 1 << KB;
+    constexpr int ACH = b3_chunk<THREADS>();
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int4 *arec = reinterpret_cast<int4 *>(smem_raw);                      // [ACH] {B row start, length, first product index, -}
+    VT *aval = reinterpret_cast<VT *>(arec + ACH);                        // [ACH]
+    VT *v = aval + ACH;                                                   // [cap] a*b of product t
+    int *c = reinterpret_cast<int *>(v + cap);                            // [cap] column of product t; later the sorted columns
+    unsigned *meta = reinterpret_cast<unsigned *>(c + cap);               // [cap] bucket << 16 | arrival
+    int *key2 = reinterpret_cast<int *>(meta + cap);                      // [cap] columns in bucket order
+    int *cnt = key2 + cap;                                                // [nb + 1] counts -> first slot of every bucket
+    unsigned *scdf = reinterpret_cast<unsigned *>(cnt + nb + 1);          // [K + 1]
+    int *scratch = reinterpret_cast<int *>(scdf + K + 1);                 // [B3_SCRATCH]
+    int *s_long = scratch + B3_SCRATCH;                                   // [B3_LONG_CAP]
+    unsigned short *perm = reinterpret_cast<unsigned short *>(s_long + B3_LONG_CAP);   // [cap] product at sorted position r
+    int *s_next = scratch + 34, *s_nlong = scratch + 35, *s_cursor = scratch + 36, *s_heads = scratch + 40;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    constexpr int DEC = CDF_BITS - KB;
+    for (int i = tid; i <= K; i += THREADS) scdf[i] = cdf.cdf[i << DEC];
+    const int sh = cdf.shift + DEC;
+    const unsigned fmask = (1u << sh) - 1u;
+
+    auto stage = [&](const int cc, const VT vv, const int t) {
+        const int i = cc >> sh;
+        const unsigned lo = scdf[i], hi = scdf[i + 1];
+        const unsigned f = lo + (unsigned)(((unsigned long long)(hi - lo) * ((unsigned)cc & fmask)) >> sh);
+        const unsigned b = __umulhi(f, (unsigned)nb);
+        const unsigned arr = (unsigned)atomicAdd(&cnt[b], 1);
+        c[t] = cc;
+        v[t] = vv;
+        meta[t] = (b << 16) | arr;
+    };
+    auto product = [&](const int e, const int t, const VT av) { stage(colB[e], av * valB[e], t); };
+
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int row = queue[q];
+        const int p = prod[row];
+        if (p <= p_lo || p > p_hi) continue;   // CTA-uniform
+        for (int i = tid; i <= nb; i += THREADS) cnt[i] = 0;
+        if (tid == 0) *s_cursor = 0;
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        // ---- the only pass over B: stage the products, count them per bucket ----
+        for (int jb = a0; jb < a1; jb += ACH) {
+            const int nch = min(ACH, a1 - jb);
+            __syncthreads();   // the previous chunk (or the previous row's emit) is done with the staging arrays
+            if (tid < nch) {
+                const int k = colA[jb + tid];
+                const int bs = rowptrB[k];
+                const int len = rowptrB[k + 1] - bs;
+                const int tb = len > 0 ? atomicAdd(s_cursor, len) : 0;
+                arec[tid] = make_int4(bs, len, tb, 0);
+                aval[tid] = valA[jb + tid];
+            }
+            if (tid == 0) {
+                *s_next = 0;
+                *s_nlong = 0;
+            }
+            __syncthreads();
+            // warps take B3_U staged B rows at a time and issue the loads of their first 32 entries together: one B
+            // row at a time left a warp with two loads in flight (ncu: half of the kernel's stall samples were
+            // long-scoreboard waits in this loop, at a fifth of its instructions)
+            for (int idx = take_next_n(s_next, lane, B3_U); idx < nch; idx = take_next_n(s_next, lane, B3_U)) {
+                int4 r[B3_U];
+                int cc[B3_U];
+                VT bv[B3_U];
+#pragma unroll
+                for (int u = 0; u < B3_U; ++u) {
+                    r[u] = idx + u < nch ? arec[idx + u] : make_int4(0, 0, 0, 0);
+                    if (r[u].y > B3_LONG) {   // warp-uniform
+                        int li = 0;
+                        if (lane == 0) li = atomicAdd(s_nlong, 1);
+                        li = __shfl_sync(FULL, li, 0);
+                        if (li < B3_LONG_CAP) {
+                            if (lane == 0) s_long[li] = idx + u;
+                            r[u].y = 0;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < B3_U; ++u) {
+                    cc[u] = 0;
+                    bv[u] = VT(0);
+                    if (lane < r[u].y) {
+                        cc[u] = colB[r[u].x + lane];
+                        bv[u] = valB[r[u].x + lane];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < B3_U; ++u)
+                    if (lane < r[u].y) stage(cc[u], aval[idx + u] * bv[u], r[u].z + lane);
+#pragma unroll
+                for (int u = 0; u < B3_U; ++u) {
+                    if (r[u].y > 32) {   // warp-uniform
+                        const VT av = aval[idx + u];
+                        for (int e = 32 + lane; e < r[u].y; e += 32) product(r[u].x + e, r[u].z + e, av);
+                    }
+                }
+            }
+            __syncthreads();
+            const int nlong = min(*s_nlong, B3_LONG_CAP);
+            for (int i = 0; i < nlong; ++i) {
+                const int4 r = arec[s_long[i]];
+                const VT av = aval[s_long[i]];
+                for (int e = tid; e < r.y; e += THREADS) product(r.x + e, r.z + e, av);
+            }
+        }
+        __syncthreads();
+        cta_exclusive_scan<THREADS>(cnt, nb + 1, scratch);   // cnt[b] = first slot of bucket b, cnt[nb] = p
+        // ---- columns into bucket order ----
+        for (int t = tid; t < p; t += THREADS) {
+            const unsigned m = meta[t];
+            key2[cnt[m >> 16] + (int)(m & 0xffffu)] = c[t];
+        }
+        __syncthreads();
+        // ---- every product ranks itself inside its bucket (ties by arrival): sorted columns + permutation ----
+        for (int t0 = warp * 32; t0 < p; t0 += THREADS) {   // warp-uniform
+            const int t = t0 + lane;
+            int s = 0, e = 0, mine = 0, cc = 0;
+            bool big = false;
+            if (t < p) {
+                const unsigned m = meta[t];
+                const int b = (int)(m >> 16);
+                s = cnt[b];
+                e = cnt[b + 1];
+                mine = s + (int)(m & 0xffffu);
+                cc = key2[mine];
+                big = e - s > B3_BIG;
+                if (!big) {
+                    // (a fixed, predicated trip count of 6 with the longer buckets on the warp path was measured
+                    // slower than this loop: too many members took the warp path)
+                    int r = s;
+                    for (int i = s; i < e; ++i) {
+                        const int ci = key2[i];
+                        r += (ci < cc || (ci == cc && i < mine)) ? 1 : 0;
+                    }
+                    c[r] = cc;
+                    perm[r] = (unsigned short)t;
+                }
+            }
+            unsigned bm = __ballot_sync(FULL, big);
+            while (bm) {   // members of long buckets: the warp counts for one member at a time
+                const int src = __ffs(bm) - 1;
+                bm &= bm - 1;
+                const int ss = __shfl_sync(FULL, s, src), ee = __shfl_sync(FULL, e, src);
+                const int mm = __shfl_sync(FULL, mine, src), xc = __shfl_sync(FULL, cc, src);
+                int part = 0;
+                for (int i = ss + lane; i < ee; i += 32) {
+                    const int ci = key2[i];
+                    part += (ci < xc || (ci == xc && i < mm)) ? 1 : 0;
+                }
+                part = __reduce_add_sync(FULL, part);
+                if (lane == src) {
+                    c[ss + part] = cc;
+                    perm[ss + part] = (unsigned short)t;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- emit: heads of equal-column runs, compacted by a ballot scan; warp w owns positions [w*L, (w+1)*L) ----
+        const int L = (((p + NW - 1) / NW) + 31) & ~31;
+        const int r0 = warp * L, r1 = min(r0 + L, p);
+        int heads = 0;
+        for (int rb = r0; rb < r1; rb += 32) {
+            const int r = rb + lane;
+            const bool head = r < r1 && (r == 0 || c[r] != c[r - 1]);
+            heads += __popc(__ballot_sync(FULL, head));
+        }
+        if (lane == 0) s_heads[warp] = heads;
+        __syncthreads();
+        int incl = lane < NW ? s_heads[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int base = __shfl_sync(FULL, incl, warp > 0 ? warp - 1 : 0);
+        if (warp == 0) base = 0;
+        const long long o = ct_base + (long long)q * ct_stride;
+        for (int rb = r0; rb < r1; rb += 32) {
+            const int r = rb + lane;
+            int cc = -1;
+            bool head = false;
+            if (r < r1) {
+                cc = c[r];
+                head = r == 0 || cc != c[r - 1];
+            }
+            const unsigned bal = __ballot_sync(FULL, head);
+            if (head) {
+                VT sum = v[perm[r]];
+                for (int rr = r + 1; rr < p && c[rr] == cc; ++rr) sum += v[perm[rr]];
+                const long long at = o + base + __popc(bal & ((1u << lane) - 1u));
+                ctcol[at] = cc;
+                ctval[at] = sum;
+            }
+            base += __popc(bal);
+        }
+        if (tid == 0) {
+            rc[row] = total;
+            ct_off[row] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_num_bucket_heavy: the same bucket sort for rows with MORE products than fit on chip (the rows the
 // reference sends through EM_mergepath_global, bhsparse_cuda.h:2270-2525, and round 1 sent through a global
 // column bitmap -- at n = 16.8 M columns, config 5, that kernel ran at 6 products/ns and held rank 0 at 99 ms
@@ -186,6 +437,9 @@ k_num_bucket(const int *__restrict__ queue, const int count, const int *__restri
 // their outputs concatenate into the sorted row.  The row's products are re-read once per slice and pass
 // (they sit in L1/L2).  A slice of a single F value that still overflows (thousands of products in one
 // column: possible only for rows of A with more entries than the capacity) is reduced column by column.
+// (Measured and dropped: finding a long B row's share of a slice by a warp-wide 32-ary search of its sorted
+// columns instead of scanning it with the filter -- 8 % slower on R-MAT 24 rank 0: the scans hit L1/L2, the searches
+// are chains of dependent loads.)
 // Direct mode: the row is staged at ct_base + [running sum of the products of the rows before it in the
 // launch, by atomic bump]; rc / ct_off as in k_num_bucket.
 // ---------------------------------------------------------------------------------------------------
@@ -204,6 +458,14 @@ k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__
     int *cnt = keys + cap;                                                    // [nb]
     int *ocnt = cnt + nb;                                                     // [nb + 1]
     int *scratch = ocnt + nb + 1;                                             // [34]
+    unsigned *scdf = reinterpret_cast<unsigned *>(scratch + 34);              // [CDF_KNOTS + 1]: the CDF table, looked up from shared memory
+    for (int i = threadIdx.x; i <= CDF_KNOTS; i += THREADS) scdf[i] = cdf.cdf[i];
+    const unsigned fmask = (1u << cdf.shift) - 1u;
+    auto feval = [&](const int c) {
+        const int i = c >> cdf.shift;
+        const unsigned lo = scdf[i], hi = scdf[i + 1];
+        return lo + (unsigned)(((unsigned long long)(hi - lo) * ((unsigned)c & fmask)) >> cdf.shift);
+    };
     __shared__ unsigned s_stack_lo[40];
     __shared__ int s_stack_lg[40];
     __shared__ long long s_row_base;
@@ -242,7 +504,7 @@ k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__
                     const int k = colA[j];
                     const int bs = rowptrB[k], be = rowptrB[k + 1];
                     for (int e = bs + lane; e < be; e += 32) {
-                        const unsigned rel = cdf_eval(cdf, colB[e]) - lo;
+                        const unsigned rel = feval(colB[e]) - lo;
                         if (lgw == 32 || (rel >> lgw) == 0u) atomicAdd(&cnt[__umulhi(lgw == 32 ? rel : rel << (32 - lgw), (unsigned)nb)], 1);
                     }
                 }
@@ -273,7 +535,7 @@ k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__
                             const int k = colA[j];
                             for (int e = rowptrB[k] + lane; e < rowptrB[k + 1]; e += 32) {
                                 const int c = colB[e];
-                                if (c > last && cdf_eval(cdf, c) == lo) mymin = min(mymin, c);
+                                if (c > last && feval(c) == lo) mymin = min(mymin, c);
                             }
                         }
                         mymin = min(mymin, __shfl_xor_sync(FULL, mymin, 16));
@@ -314,7 +576,7 @@ k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__
                     const int bs = rowptrB[k], be = rowptrB[k + 1];
                     for (int e = bs + lane; e < be; e += 32) {
                         const int c = colB[e];
-                        const unsigned rel = cdf_eval(cdf, c) - lo;
+                        const unsigned rel = feval(c) - lo;
                         if (lgw == 32 || (rel >> lgw) == 0u) {
                             const int slot = atomicAdd(&cnt[__umulhi(lgw == 32 ? rel : rel << (32 - lgw), (unsigned)nb)], 1);
                             keys[slot] = c;

@@ -246,6 +246,43 @@ def test_direct_mode_wide_bins(dt, monkeypatch):
     assert all(not ((st["direct_bin_mask"] >> b) & 1) for b in range(4, 10))
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_wide_rows_bucket_sort_edges(dt, monkeypatch):
+    """k_num_bucket3 (csrc/stage_bucket.cuh) beyond uniform rows: (a) rows of A with more entries than one
+    staging chunk and B rows longer than the whole-CTA threshold (512), (b) a hub column present in every B
+    row -- hundreds of equal columns in ONE bucket of every output row (the warp-cooperative ranking and the
+    run-summing emit), (c) both variants of the first bucket kernel as a cross-check (BHB200_BUCKET_V=1)."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("general path only")
+    rows = 5 * 4200
+    # (a) many short B rows per A row + a few very long B rows referenced by every fifth A row
+    k, n = 30000, 2_500_000
+    b_len = np.full(k, 3)
+    b_len[:40] = np.array([600, 900, 1500, 2500])[np.arange(40) % 4]
+    B = gen.random_csr(k, n, b_len, seed=52, value_seed=53, dtype=dt)
+    per_row = np.array([150, 300, 700, 40, 1100])[np.arange(rows) % 5]
+    A = gen.random_csr(rows, k - 40, per_row, seed=51, dtype=dt)
+    # shift A's columns past the long rows, then give every fifth row one of them (rows stay sorted: 0..39 < 40)
+    colA = A.col + 40
+    first = A.rowptr[:-1][::5]
+    colA[first] = np.arange(first.size) % 40
+    A = CSR(rows, k, A.rowptr, colA.astype(np.int32), A.val)
+    st = _check(A, B, f"bucket chunks + long B rows {dt.__name__}")
+    assert st["direct_rows"] >= 4 * 4200
+    # (b) hub column: every B row holds column 7 and eleven random ones
+    k = 20000
+    rng = np.random.default_rng(6)
+    others = 8 + np.sort(rng.choice((n - 8) // 11, size=(k, 11)), axis=1) * 11 + np.arange(11)
+    cols = np.concatenate([np.full((k, 1), 7), others], axis=1)
+    B = CSR(k, n, (np.arange(k + 1) * 12).astype(np.int32), cols.reshape(-1).astype(np.int32), gen.int_values(12 * k, 9, dt))
+    per_row = np.array([50, 90, 180, 330, 600])[np.arange(rows) % 5]
+    A = gen.random_csr(rows, k, per_row, seed=54, dtype=dt)
+    st = _check(A, B, f"bucket hub column {dt.__name__}")
+    assert st["direct_rows"] >= 4 * 4200
+    monkeypatch.setenv("BHB200_BUCKET_V", "1")
+    _check(A, B, f"bucket v1 hub column {dt.__name__}")
+
+
 def test_direct_mode_off_matches(monkeypatch):
     if os.environ.get("BHB200_PATTERN") != "off":
         pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
