@@ -163,6 +163,8 @@ struct DirectOut {
     const int *prod = nullptr;
     int p_lo = 0, p_hi = 0x7fffffff;
     int ct_stride = 0;       // 0: the kernel's own capacity
+    unsigned long long *bump = nullptr;   // k_num_bucket3: stage rows by atomic bump of this cursor (products each) instead of q * ct_stride
+    const int *count_dev = nullptr;       // k_num_bucket_heavy as the retry kernel: number of queued rows, on the device
 };
 
 // Word lists: the symbolic range kernel stores, per row, the non-empty 64-column words of
@@ -590,6 +592,12 @@ cudaError_t launch_num_bucket_heavy_f32(const LaunchCtx &lc, const int *queue, i
                                         const unsigned *cdf, int cdf_shift, unsigned long long *cursor);
 cudaError_t launch_num_bucket_heavy_f64(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
                                         const unsigned *cdf, int cdf_shift, unsigned long long *cursor);
+// second formulation (k_num_bucket_heavy2): rows with more than d.p_lo products, partitioned by slice through their own
+// staging area; rows it cannot slice go to d.retry_queue / d.retry_cnt for launch_num_bucket_heavy_* (d.count_dev)
+cudaError_t launch_num_bucket_heavy2_f32(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                         const unsigned *cdf, int cdf_shift, unsigned long long *cursor);
+cudaError_t launch_num_bucket_heavy2_f64(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                         const unsigned *cdf, int cdf_shift, unsigned long long *cursor);
 // column CDF of the intermediate products (stage_bucket.cu): colcountA [k+1] ints, hist [4096] u64, cdf [4097] u32
 cudaError_t launch_build_cdf(const LaunchCtx &lc, int m, int k, int n, int nnzA, Csr A, Csr B, int *colcountA,
                              unsigned long long *hist, unsigned *cdf, int *shift_out);

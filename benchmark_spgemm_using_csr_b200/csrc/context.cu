@@ -756,10 +756,9 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                 top_wide = ((spec_mask >> b) & 1u) && spec_wide[b];
                 break;
             }
-        // (measured, profiles/r02_notes.md: the sliced bucket sort runs at ~13 products/ns whatever n is; the
-        // two-pass tables + global column bitmap at 16 products/ns for n = 2 M columns, 14 at 4 M, 7 at 16.8 M)
-        const bool many_columns = ctx->n > (1 << 22) || getenv("BHB200_DEBUG_FORCE_HEAVY") != nullptr;
-        if (top_wide && many_columns && ctx->bucket_enable && ctx->bucket_heavy && ctx->direct_wide) {
+        // (k_num_bucket_heavy2, measured on R-MAT 21, n = 2 M columns: 4.0 ms for these rows against 7.0 ms through the
+        // two-pass tables + global column bitmap, whose cost also grows with n -- profiles/r02_notes.md section 5)
+        if (top_wide && ctx->bucket_enable && ctx->bucket_heavy && ctx->direct_wide) {
             heavy_base = ct_entries;
             for (int b = SB_B16384; b <= SB_LARGE; ++b) {
                 if (hc.sym_bin[b] <= 0) continue;
@@ -833,6 +832,44 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                                 ctx->cdf_hist.as<unsigned long long>(), ctx->cdf_tab.as<unsigned>(), &cdf_shift),
                "column CDF");
     }
+    // Rows with more products than the on-chip tables hold (bins SB_B16384 .. SB_LARGE), single pass, staged by atomic
+    // bump at heavy_base: rows of at most 8192 products by k_num_bucket3 itself, the rest by k_num_bucket_heavy2
+    // (partitioned by slice through the row's own staging area), what that kernel cannot slice by k_num_bucket_heavy
+    // (BHB200_HEAVY_V=1: everything by k_num_bucket_heavy).
+    static const bool heavy_v1 = [] { const char *e = getenv("BHB200_HEAVY_V"); return e && atoi(e) == 1; }();
+    auto run_heavy_bin = [&](const int b) -> cudaError_t {
+        const bool f64 = ctx->dtype == BHB200_DTYPE_F64;
+        const unsigned *cdf = ctx->cdf_tab.as<unsigned>();
+        const int *bq = queue + so.off[b];
+        const int rows = hc.sym_bin[b];
+        DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, heavy_base, nullptr, nullptr};
+        d.prod = prod;
+        cudaError_t e;
+        if (heavy_v1)
+            return f64 ? launch_num_bucket_heavy_f64(lc, bq, rows, ctx->A, ctx->B, d, cdf, cdf_shift, &d_ctr->heavy_cursor)
+                       : launch_num_bucket_heavy_f32(lc, bq, rows, ctx->A, ctx->B, d, cdf, cdf_shift, &d_ctr->heavy_cursor);
+        int p_lo = 0;
+        static const bool bucket_v1 = [] { const char *e = getenv("BHB200_BUCKET_V"); return e && atoi(e) == 1; }();
+        if (b == SB_B16384 && !bucket_v1) {   // 6144 < products <= 12288: up to 8192 fit k_num_bucket3's largest capacity
+            DirectOut d3 = d;
+            d3.p_lo = 0;
+            d3.p_hi = 8192;
+            d3.bump = &d_ctr->heavy_cursor;
+            e = f64 ? launch_num_bucket_f64(lc, 8192, bq, rows, ctx->A, ctx->B, d3, cdf, cdf_shift)
+                    : launch_num_bucket_f32(lc, 8192, bq, rows, ctx->A, ctx->B, d3, cdf, cdf_shift);
+            if (e != cudaSuccess) return e;
+            p_lo = 8192;
+        }
+        d.p_lo = p_lo;
+        d.retry_queue = ctx->retry_q.as<int>() + so.off[b];
+        d.retry_cnt = &d_ctr->retry_cnt[b];
+        e = f64 ? launch_num_bucket_heavy2_f64(lc, bq, rows, ctx->A, ctx->B, d, cdf, cdf_shift, &d_ctr->heavy_cursor)
+                : launch_num_bucket_heavy2_f32(lc, bq, rows, ctx->A, ctx->B, d, cdf, cdf_shift, &d_ctr->heavy_cursor);
+        if (e != cudaSuccess) return e;
+        d.count_dev = d.retry_cnt;
+        return f64 ? launch_num_bucket_heavy_f64(lc, d.retry_queue, rows, ctx->A, ctx->B, d, cdf, cdf_shift, &d_ctr->heavy_cursor)
+                   : launch_num_bucket_heavy_f32(lc, d.retry_queue, rows, ctx->A, ctx->B, d, cdf, cdf_shift, &d_ctr->heavy_cursor);
+    };
     // ---- stage 2: symbolic, one launch per non-empty bin (direct-mode bins: the numeric kernel itself) ----
     memset(ctx->ev_bin_used, 0, sizeof(ctx->ev_bin_used));
     if (hc.sym_bin[SB_ESC] > 0) CU(stamp(ctx, 0, SB_ESC), "event");
@@ -840,14 +877,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     for (int b = SB_G128; b <= SB_B32768; ++b) {
         if (hc.sym_bin[b] > 0) CU(stamp(ctx, 0, b), "event");
         if (((spec_mask >> b) & 1u) && spec_heavy[b]) {
-            DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, heavy_base, nullptr, nullptr};
-            d.prod = prod;
-            if (ctx->dtype == BHB200_DTYPE_F64)
-                CU(launch_num_bucket_heavy_f64(lc, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, &d_ctr->heavy_cursor),
-                   "heavy bucket numeric f64");
-            else
-                CU(launch_num_bucket_heavy_f32(lc, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, &d_ctr->heavy_cursor),
-                   "heavy bucket numeric f32");
+            CU(run_heavy_bin(b), "heavy rows");
             st.direct_rows += hc.sym_bin[b];
             continue;
         }
@@ -891,14 +921,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     }
     if (hc.sym_bin[SB_LARGE] > 0 && ((spec_mask >> SB_LARGE) & 1u) && spec_heavy[SB_LARGE]) {
         CU(stamp(ctx, 0, SB_LARGE), "event");
-        DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, heavy_base, nullptr, nullptr};
-        d.prod = prod;
-        if (ctx->dtype == BHB200_DTYPE_F64)
-            CU(launch_num_bucket_heavy_f64(lc, queue + so.off[SB_LARGE], hc.sym_bin[SB_LARGE], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, &d_ctr->heavy_cursor),
-               "heavy bucket numeric f64");
-        else
-            CU(launch_num_bucket_heavy_f32(lc, queue + so.off[SB_LARGE], hc.sym_bin[SB_LARGE], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, &d_ctr->heavy_cursor),
-               "heavy bucket numeric f32");
+        CU(run_heavy_bin(SB_LARGE), "heavy rows");
         st.direct_rows += hc.sym_bin[SB_LARGE];
     } else if (hc.sym_bin[SB_LARGE] > 0) {
         rc = reserve_large_scratch(ctx, false);

@@ -213,17 +213,122 @@ inline size_t b3_smem_bytes(const int cap, const int nb, const int knots)
            (size_t)(knots + 1) * 4 + (size_t)(B3_SCRATCH + B3_LONG_CAP) * 4 + (size_t)cap * 2;
 }
 
+// The sort of k_num_bucket3 after the products are staged: c[t], v[t], meta[t] = bucket << 16 | arrival for the p
+// products, cnt[0..nb] = products per bucket (cnt[nb] = 0); a barrier has been passed.  Scans the counts, copies
+// the columns into bucket order, ranks every product inside its bucket, then emits the heads of equal-column
+// runs (values summed) to ctcol/ctval[o ..).  Returns the number of entries written (CTA-uniform).  The caller
+// needs a barrier before it touches the arrays again.
+template <typename VT, int THREADS>
+__device__ __forceinline__ int b3_sort_emit(VT *v, int *c, unsigned *meta, int *key2, int *cnt, unsigned short *perm, int *scratch,
+                                            const int p, const int nb, int *__restrict__ ctcol, VT *__restrict__ ctval,
+                                            const long long o)
+{
+    constexpr int NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *s_heads = scratch + 40;
+    cta_exclusive_scan<THREADS>(cnt, nb + 1, scratch);   // cnt[b] = first slot of bucket b, cnt[nb] = p
+    // ---- columns into bucket order ----
+    for (int t = tid; t < p; t += THREADS) {
+        const unsigned m = meta[t];
+        key2[cnt[m >> 16] + (int)(m & 0xffffu)] = c[t];
+    }
+    __syncthreads();
+    // ---- every product ranks itself inside its bucket (ties by arrival): sorted columns + permutation ----
+    for (int t0 = warp * 32; t0 < p; t0 += THREADS) {   // warp-uniform
+        const int t = t0 + lane;
+        int s = 0, e = 0, mine = 0, cc = 0;
+        bool big = false;
+        if (t < p) {
+            const unsigned m = meta[t];
+            const int b = (int)(m >> 16);
+            s = cnt[b];
+            e = cnt[b + 1];
+            mine = s + (int)(m & 0xffffu);
+            cc = key2[mine];
+            big = e - s > B3_BIG;
+            if (!big) {
+                // (a fixed, predicated trip count of 6 with the longer buckets on the warp path was measured
+                // slower than this loop: too many members took the warp path)
+                int r = s;
+                for (int i = s; i < e; ++i) {
+                    const int ci = key2[i];
+                    r += (ci < cc || (ci == cc && i < mine)) ? 1 : 0;
+                }
+                c[r] = cc;
+                perm[r] = (unsigned short)t;
+            }
+        }
+        unsigned bm = __ballot_sync(FULL, big);
+        while (bm) {   // members of long buckets: the warp counts for one member at a time
+            const int src = __ffs(bm) - 1;
+            bm &= bm - 1;
+            const int ss = __shfl_sync(FULL, s, src), ee = __shfl_sync(FULL, e, src);
+            const int mm = __shfl_sync(FULL, mine, src), xc = __shfl_sync(FULL, cc, src);
+            int part = 0;
+            for (int i = ss + lane; i < ee; i += 32) {
+                const int ci = key2[i];
+                part += (ci < xc || (ci == xc && i < mm)) ? 1 : 0;
+            }
+            part = __reduce_add_sync(FULL, part);
+            if (lane == src) {
+                c[ss + part] = cc;
+                perm[ss + part] = (unsigned short)t;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- emit: heads of equal-column runs, compacted by a ballot scan; warp w owns positions [w*L, (w+1)*L) ----
+    const int L = (((p + NW - 1) / NW) + 31) & ~31;
+    const int r0 = warp * L, r1 = min(r0 + L, p);
+    int heads = 0;
+    for (int rb = r0; rb < r1; rb += 32) {
+        const int r = rb + lane;
+        const bool head = r < r1 && (r == 0 || c[r] != c[r - 1]);
+        heads += __popc(__ballot_sync(FULL, head));
+    }
+    if (lane == 0) s_heads[warp] = heads;
+    __syncthreads();
+    int incl = lane < NW ? s_heads[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += y;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int base = __shfl_sync(FULL, incl, warp > 0 ? warp - 1 : 0);
+    if (warp == 0) base = 0;
+    for (int rb = r0; rb < r1; rb += 32) {
+        const int r = rb + lane;
+        int cc = -1;
+        bool head = false;
+        if (r < r1) {
+            cc = c[r];
+            head = r == 0 || cc != c[r - 1];
+        }
+        const unsigned bal = __ballot_sync(FULL, head);
+        if (head) {
+            VT sum = v[perm[r]];
+            for (int rr = r + 1; rr < p && c[rr] == cc; ++rr) sum += v[perm[rr]];
+            const long long at = o + base + __popc(bal & ((1u << lane) - 1u));
+            ctcol[at] = cc;
+            ctval[at] = sum;
+        }
+        base += __popc(bal);
+    }
+    return total;
+}
+
 template <typename VT, int THREADS, int KB>
 __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 1536 / THREADS)   // 1536 threads per SM, or one full-size CTA
 k_num_bucket3(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA, const int *__restrict__ colA,
               const VT *__restrict__ valA, const int *__restrict__ rowptrB, const int *__restrict__ colB,
               const VT *__restrict__ valB, const ColumnCdf cdf, const int cap, const int nb, int *__restrict__ rc,
               long long *__restrict__ ct_off, int *__restrict__ ctcol, VT *__restrict__ ctval, const long long ct_base,
-              const int *__restrict__ prod, const int p_lo, const int p_hi, const int ct_stride)
+              const int *__restrict__ prod, const int p_lo, const int p_hi, const int ct_stride,
+              unsigned long long *__restrict__ cursor)   // cursor != nullptr: rows staged by atomic bump (p entries each) instead of q * ct_stride
 {
     constexpr int K = 1 << KB;
     constexpr int ACH = b3_chunk<THREADS>();
-    constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int4 *arec = reinterpret_cast<int4 *>(smem_raw);                      // [ACH] {B row start, length, first product index, -}
     VT *aval = reinterpret_cast<VT *>(arec + ACH);                        // [ACH]
@@ -236,8 +341,9 @@ k_num_bucket3(const int *__restrict__ queue, const int count, const int *__restr
     int *scratch = reinterpret_cast<int *>(scdf + K + 1);                 // [B3_SCRATCH]
     int *s_long = scratch + B3_SCRATCH;                                   // [B3_LONG_CAP]
     unsigned short *perm = reinterpret_cast<unsigned short *>(s_long + B3_LONG_CAP);   // [cap] product at sorted position r
-    int *s_next = scratch + 34, *s_nlong = scratch + 35, *s_cursor = scratch + 36, *s_heads = scratch + 40;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *s_next = scratch + 34, *s_nlong = scratch + 35, *s_cursor = scratch + 36;
+    __shared__ long long s_bump[1];
+    const int tid = threadIdx.x, lane = tid & 31;
 
     constexpr int DEC = CDF_BITS - KB;
     for (int i = tid; i <= K; i += THREADS) scdf[i] = cdf.cdf[i << DEC];
@@ -261,7 +367,10 @@ k_num_bucket3(const int *__restrict__ queue, const int count, const int *__restr
         const int p = prod[row];
         if (p <= p_lo || p > p_hi) continue;   // CTA-uniform
         for (int i = tid; i <= nb; i += THREADS) cnt[i] = 0;
-        if (tid == 0) *s_cursor = 0;
+        if (tid == 0) {
+            *s_cursor = 0;
+            if (cursor) s_bump[0] = ct_base + (long long)atomicAdd(cursor, (unsigned long long)p);
+        }
         const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
         // ---- the only pass over B: stage the products, count them per bucket ----
         for (int jb = a0; jb < a1; jb += ACH) {
@@ -329,96 +438,8 @@ k_num_bucket3(const int *__restrict__ queue, const int count, const int *__restr
             }
         }
         __syncthreads();
-        cta_exclusive_scan<THREADS>(cnt, nb + 1, scratch);   // cnt[b] = first slot of bucket b, cnt[nb] = p
-        // ---- columns into bucket order ----
-        for (int t = tid; t < p; t += THREADS) {
-            const unsigned m = meta[t];
-            key2[cnt[m >> 16] + (int)(m & 0xffffu)] = c[t];
-        }
-        __syncthreads();
-        // ---- every product ranks itself inside its bucket (ties by arrival): sorted columns + permutation ----
-        for (int t0 = warp * 32; t0 < p; t0 += THREADS) {   // warp-uniform
-            const int t = t0 + lane;
-            int s = 0, e = 0, mine = 0, cc = 0;
-            bool big = false;
-            if (t < p) {
-                const unsigned m = meta[t];
-                const int b = (int)(m >> 16);
-                s = cnt[b];
-                e = cnt[b + 1];
-                mine = s + (int)(m & 0xffffu);
-                cc = key2[mine];
-                big = e - s > B3_BIG;
-                if (!big) {
-                    // (a fixed, predicated trip count of 6 with the longer buckets on the warp path was measured
-                    // slower than this loop: too many members took the warp path)
-                    int r = s;
-                    for (int i = s; i < e; ++i) {
-                        const int ci = key2[i];
-                        r += (ci < cc || (ci == cc && i < mine)) ? 1 : 0;
-                    }
-                    c[r] = cc;
-                    perm[r] = (unsigned short)t;
-                }
-            }
-            unsigned bm = __ballot_sync(FULL, big);
-            while (bm) {   // members of long buckets: the warp counts for one member at a time
-                const int src = __ffs(bm) - 1;
-                bm &= bm - 1;
-                const int ss = __shfl_sync(FULL, s, src), ee = __shfl_sync(FULL, e, src);
-                const int mm = __shfl_sync(FULL, mine, src), xc = __shfl_sync(FULL, cc, src);
-                int part = 0;
-                for (int i = ss + lane; i < ee; i += 32) {
-                    const int ci = key2[i];
-                    part += (ci < xc || (ci == xc && i < mm)) ? 1 : 0;
-                }
-                part = __reduce_add_sync(FULL, part);
-                if (lane == src) {
-                    c[ss + part] = cc;
-                    perm[ss + part] = (unsigned short)t;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- emit: heads of equal-column runs, compacted by a ballot scan; warp w owns positions [w*L, (w+1)*L) ----
-        const int L = (((p + NW - 1) / NW) + 31) & ~31;
-        const int r0 = warp * L, r1 = min(r0 + L, p);
-        int heads = 0;
-        for (int rb = r0; rb < r1; rb += 32) {
-            const int r = rb + lane;
-            const bool head = r < r1 && (r == 0 || c[r] != c[r - 1]);
-            heads += __popc(__ballot_sync(FULL, head));
-        }
-        if (lane == 0) s_heads[warp] = heads;
-        __syncthreads();
-        int incl = lane < NW ? s_heads[lane] : 0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += y;
-        }
-        const int total = __shfl_sync(FULL, incl, 31);
-        int base = __shfl_sync(FULL, incl, warp > 0 ? warp - 1 : 0);
-        if (warp == 0) base = 0;
-        const long long o = ct_base + (long long)q * ct_stride;
-        for (int rb = r0; rb < r1; rb += 32) {
-            const int r = rb + lane;
-            int cc = -1;
-            bool head = false;
-            if (r < r1) {
-                cc = c[r];
-                head = r == 0 || cc != c[r - 1];
-            }
-            const unsigned bal = __ballot_sync(FULL, head);
-            if (head) {
-                VT sum = v[perm[r]];
-                for (int rr = r + 1; rr < p && c[rr] == cc; ++rr) sum += v[perm[rr]];
-                const long long at = o + base + __popc(bal & ((1u << lane) - 1u));
-                ctcol[at] = cc;
-                ctval[at] = sum;
-            }
-            base += __popc(bal);
-        }
+        const long long o = cursor ? s_bump[0] : ct_base + (long long)q * ct_stride;
+        const int total = b3_sort_emit<VT, THREADS>(v, c, meta, key2, cnt, perm, scratch, p, nb, ctcol, ctval, o);
         if (tid == 0) {
             rc[row] = total;
             ct_off[row] = o;
@@ -450,7 +471,7 @@ k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__
                    const int *__restrict__ colB, const VT *__restrict__ valB, const ColumnCdf cdf, const int cap,
                    const int nb, int *__restrict__ rc, long long *__restrict__ ct_off, int *__restrict__ ctcol,
                    VT *__restrict__ ctval, const long long ct_base, unsigned long long *__restrict__ cursor,
-                   const int *__restrict__ prod)
+                   const int *__restrict__ prod, const int *__restrict__ count_dev)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VT *vals = reinterpret_cast<VT *>(smem_raw);                              // [cap]
@@ -472,8 +493,9 @@ k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__
     __shared__ int s_min;
     __shared__ double s_sum;
     const int lane = threadIdx.x & 31;
+    const int nrows = count_dev ? min(*count_dev, count) : count;   // (retry kernel: the queue was filled on the device)
 
-    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+    for (int q = blockIdx.x; q < nrows; q += gridDim.x) {
         const int row = queue[q];
         const int p = prod[row];
         const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
@@ -632,6 +654,145 @@ k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__
             ct_off[row] = o;
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_num_bucket_heavy2: rows with more products than fit on chip, second formulation.  k_num_bucket_heavy
+// re-reads ALL of a row's B rows twice per slice (count + scatter with the slice's filter): a row of 200 000
+// products in 40 slices is walked 80 times (R-MAT 24, rank 0: 31 of 62 ms in these rows).  Here the row is
+//   1. counted per slice (one pass; a slice that would overflow the chip doubles the slice count, once),
+//   2. scattered into its own staging area in global memory, partitioned by slice (one pass),
+//   3. sorted slice by slice: the slice's segment is loaded densely, bucketed, ranked and emitted by
+//      b3_sort_emit, compacted, in place -- the output of slices 0..s never reaches the input of slice s+1.
+// Rows whose slices still overflow (one column carrying more products than the chip holds, ...) are handed to
+// k_num_bucket_heavy through a retry queue before anything is written or allocated for them.
+// Rows of at most p_lo products are skipped (they are taken by k_num_bucket3 in the same staging area).
+// ---------------------------------------------------------------------------------------------------
+constexpr int H2_MAX_LG = 11;   // at most 2048 slices per row (16.7 M products); longer rows -> retry queue
+
+template <typename VT>
+inline size_t h2_smem_bytes(const int cap, const int nb)
+{
+    return (size_t)cap * (sizeof(VT) + 12) + (size_t)(nb + 1) * 4 + (size_t)(CDF_KNOTS + 1) * 4 + (size_t)B3_SCRATCH * 4 +
+           (size_t)((1 << H2_MAX_LG) + 1) * 4 + (size_t)cap * 2;
+}
+
+template <typename VT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_num_bucket_heavy2(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA,
+                    const int *__restrict__ colA, const VT *__restrict__ valA, const int *__restrict__ rowptrB,
+                    const int *__restrict__ colB, const VT *__restrict__ valB, const ColumnCdf cdf, const int cap,
+                    const int nb, int *__restrict__ rc, long long *__restrict__ ct_off, int *__restrict__ ctcol,
+                    VT *__restrict__ ctval, const long long ct_base, unsigned long long *__restrict__ cursor,
+                    const int *__restrict__ prod, const int p_lo, int *__restrict__ retry_queue, int *__restrict__ retry_cnt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VT *v = reinterpret_cast<VT *>(smem_raw);                                 // [cap]
+    int *c = reinterpret_cast<int *>(v + cap);                                // [cap]
+    unsigned *meta = reinterpret_cast<unsigned *>(c + cap);                   // [cap]
+    int *key2 = reinterpret_cast<int *>(meta + cap);                          // [cap]
+    int *cnt = key2 + cap;                                                    // [nb + 1]
+    unsigned *scdf = reinterpret_cast<unsigned *>(cnt + nb + 1);              // [CDF_KNOTS + 1]
+    int *scratch = reinterpret_cast<int *>(scdf + CDF_KNOTS + 1);             // [B3_SCRATCH]
+    int *hist = scratch + B3_SCRATCH;                                         // [2^H2_MAX_LG + 1] products per slice -> segment ends
+    unsigned short *perm = reinterpret_cast<unsigned short *>(hist + (1 << H2_MAX_LG) + 1);   // [cap]
+    __shared__ long long s_row_base;
+    __shared__ int s_max;
+    int *s_next = scratch + 34;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    for (int i = tid; i <= CDF_KNOTS; i += THREADS) scdf[i] = cdf.cdf[i];
+    const unsigned fmask = (1u << cdf.shift) - 1u;
+    auto feval = [&](const int col) {
+        const int i = col >> cdf.shift;
+        const unsigned lo = scdf[i], hi = scdf[i + 1];
+        return lo + (unsigned)(((unsigned long long)(hi - lo) * ((unsigned)col & fmask)) >> cdf.shift);
+    };
+
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        const int row = queue[q];
+        const int p = prod[row];
+        if (p <= p_lo) continue;   // CTA-uniform
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        // slices: 2^lg with 1.5x headroom; one more doubling if the row's own distribution overflows a slice
+        int lg = 0;
+        while (lg < H2_MAX_LG && ((long long)cap << lg) * 2 < (long long)p * 3) ++lg;
+        bool fits = ((long long)cap << lg) >= (long long)p;
+        for (int attempt = 0; fits && attempt < 2; ++attempt) {
+            const int S = 1 << lg;
+            __syncthreads();
+            for (int i = tid; i <= S; i += THREADS) hist[i] = 0;
+            if (tid == 0) {
+                *s_next = 0;
+                s_max = 0;
+            }
+            __syncthreads();
+            for (int j = a0 + take_next(s_next, lane); j < a1; j = a0 + take_next(s_next, lane)) {
+                const int k = colA[j];
+                const int bs = rowptrB[k], be = rowptrB[k + 1];
+                for (int e = bs + lane; e < be; e += 32) atomicAdd(&hist[lg ? feval(colB[e]) >> (32 - lg) : 0], 1);
+            }
+            __syncthreads();
+            int mx = 0;
+            for (int i = tid; i < S; i += THREADS) mx = max(mx, hist[i]);
+            mx = __reduce_max_sync(FULL, mx);
+            if (lane == 0 && mx > 0) atomicMax(&s_max, mx);
+            __syncthreads();
+            if (s_max <= cap) break;
+            if (attempt == 0 && lg < H2_MAX_LG) ++lg; else fits = false;
+        }
+        if (!fits) {   // CTA-uniform: nothing was allocated or written for this row
+            if (tid == 0) retry_queue[atomicAdd(retry_cnt, 1)] = row;
+            continue;
+        }
+        const int S = 1 << lg;
+        cta_exclusive_scan<THREADS>(hist, S + 1, scratch);   // hist[s] = first entry of slice s, hist[S] = p
+        if (tid == 0) {
+            s_row_base = ct_base + (long long)atomicAdd(cursor, (unsigned long long)p);
+            *s_next = 0;
+        }
+        __syncthreads();
+        const long long o = s_row_base;
+        // ---- scatter into the row's staging area, partitioned by slice; afterwards hist[s] = END of slice s ----
+        for (int j = a0 + take_next(s_next, lane); j < a1; j = a0 + take_next(s_next, lane)) {
+            const int k = colA[j];
+            const VT av = valA[j];
+            const int bs = rowptrB[k], be = rowptrB[k + 1];
+            for (int e = bs + lane; e < be; e += 32) {
+                const int col = colB[e];
+                const int at = atomicAdd(&hist[lg ? feval(col) >> (32 - lg) : 0], 1);
+                ctcol[o + at] = col;
+                ctval[o + at] = av * valB[e];
+            }
+        }
+        __syncthreads();   // (the CTA's own global writes are visible to it after the barrier)
+        int written = 0;   // CTA-uniform
+        for (int s = 0; s < S; ++s) {
+            const int first = s ? hist[s - 1] : 0;
+            const int n = hist[s] - first;
+            if (n == 0) continue;
+            for (int i = tid; i <= nb; i += THREADS) cnt[i] = 0;
+            __syncthreads();
+            const unsigned lo = lg ? (unsigned)s << (32 - lg) : 0u;
+            for (int t = tid; t < n; t += THREADS) {
+                const int col = ctcol[o + first + t];
+                const VT val = ctval[o + first + t];
+                const unsigned rel = feval(col) - lo;
+                const unsigned b = __umulhi(lg ? rel << lg : rel, (unsigned)nb);
+                const unsigned arr = (unsigned)atomicAdd(&cnt[b], 1);
+                c[t] = col;
+                v[t] = val;
+                meta[t] = (b << 16) | arr;
+            }
+            __syncthreads();
+            written += b3_sort_emit<VT, THREADS>(v, c, meta, key2, cnt, perm, scratch, n, nb, ctcol, ctval, o + written);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            rc[row] = written;
+            ct_off[row] = o;
+        }
     }
 }
 

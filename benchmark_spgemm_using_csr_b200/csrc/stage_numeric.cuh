@@ -813,7 +813,7 @@ static cudaError_t launch_num_bucket_tt(const LaunchCtx &lc, int cap, const int 
         ++*lc.launches;
         k3<<<(int)blocks3, THREADS, smem3, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
                                                          (const VT *)B.val, cdf, cap, nb3, d.rc, d.ct_off, d.ctcol, (VT *)d.ctval,
-                                                         d.ct_base, d.prod, d.p_lo, d.p_hi, d.ct_stride ? d.ct_stride : cap);
+                                                         d.ct_base, d.prod, d.p_lo, d.p_hi, d.ct_stride ? d.ct_stride : cap, d.bump);
         return cudaGetLastError();
     }
     static const int div = [] { const char *e = getenv("BHB200_BUCKET_DIV"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }();
@@ -880,7 +880,28 @@ static cudaError_t launch_num_bucket_heavy_t(const LaunchCtx &lc, const int *que
     ++*lc.launches;
     kern<<<(int)blocks, THREADS, smem, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
                                                     (const VT *)B.val, cdf, cap, nb, d.rc, d.ct_off, d.ctcol, (VT *)d.ctval,
-                                                    d.ct_base, cursor, d.prod);
+                                                    d.ct_base, cursor, d.prod, d.count_dev);
+    return cudaGetLastError();
+}
+
+template <typename VT>
+static cudaError_t launch_num_bucket_heavy2_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                              ColumnCdf cdf, unsigned long long *cursor)
+{
+    if (count <= 0) return cudaSuccess;
+    constexpr int THREADS = 1024;
+    constexpr int cap = 8192, nb = cap / 2;   // entries of a slice on chip (22 / 18 bytes each), buckets per slice
+    const size_t smem = h2_smem_bytes<VT>(cap, nb);
+    auto kern = k_num_bucket_heavy2<VT, THREADS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long blocks = count;
+    const long long lim = (long long)lc.sm_count * resident_blocks(kern, THREADS, smem);
+    if (blocks > lim) blocks = lim;
+    ++*lc.launches;
+    kern<<<(int)blocks, THREADS, smem, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
+                                                    (const VT *)B.val, cdf, cap, nb, d.rc, d.ct_off, d.ctcol, (VT *)d.ctval,
+                                                    d.ct_base, cursor, d.prod, d.p_lo, d.retry_queue, d.retry_cnt);
     return cudaGetLastError();
 }
 

@@ -55,4 +55,10 @@ cudaError_t launch_num_bucket_heavy_f64(const LaunchCtx &lc, const int *queue, i
     return launch_num_bucket_heavy_t<double>(lc, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift}, cursor);
 }
 
+cudaError_t launch_num_bucket_heavy2_f64(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                         const unsigned *cdf, int cdf_shift, unsigned long long *cursor)
+{
+    return launch_num_bucket_heavy2_t<double>(lc, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift}, cursor);
+}
+
 }  // namespace bhb
