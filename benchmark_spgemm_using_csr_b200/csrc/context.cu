@@ -59,6 +59,7 @@ void release_operands(bhb200_ctx *ctx)
     ctx->have_data = false;
     ctx->borrowed = false;
     ctx->aliased = false;
+    ctx->slice_e0 = -1;
     ctx->have_C = false;
     ctx->last_pattern = false;
     ctx->nnzC = 0;
@@ -313,12 +314,15 @@ int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab, bool specula
     const PatternPlan &plan = ctx->plan;
     cudaStream_t s = ctx->stream;
     bhb200_stats &st = ctx->stats;
+    // multi-GPU row block of a square product: A's entries are a slice of B's arrays, so the codes of B serve A too
+    // (one pass instead of two) as long as both operands index the same offset list
+    const bool slice = !same_ab && ctx->slice_e0 >= 0 && ctx->slice_range.p && plan.DA == plan.DB;
     // workspace; any allocation failure falls back to the general path
     const size_t need_tab = plan.blob.size();
     const bool had_tables = ctx->pat_tables.cap >= need_tab && plan.reused;
     if (ctx->pat_tables.reserve(need_tab, &ctx->dev_bytes) != cudaSuccess ||
         ctx->pat_tb.reserve((size_t)ctx->nnzB + 16, &ctx->dev_bytes) != cudaSuccess ||
-        (!same_ab && ctx->pat_ta.reserve((size_t)ctx->nnzA + 16, &ctx->dev_bytes) != cudaSuccess) ||
+        (!same_ab && !slice && ctx->pat_ta.reserve((size_t)ctx->nnzA + 16, &ctx->dev_bytes) != cudaSuccess) ||
         ctx->pat_maskB.reserve(((size_t)ctx->k + 1) * 8, &ctx->dev_bytes) != cudaSuccess ||
         ctx->pat_fullbits.reserve(((size_t)ctx->k / 32 + 2) * 4, &ctx->dev_bytes) != cudaSuccess ||
         ctx->pat_outmask.reserve(((size_t)ctx->m + 1) * plan.nw * 4, &ctx->dev_bytes) != cudaSuccess) {
@@ -331,13 +335,15 @@ int run_pattern(bhb200_ctx *ctx, const LaunchCtx &lc, bool same_ab, bool specula
     PatTables t = pattern_tables(plan, ctx->pat_tables.as<unsigned char>());
     t.fullbits = ctx->pat_fullbits.as<unsigned>();
     unsigned char *tb = ctx->pat_tb.as<unsigned char>();
-    unsigned char *ta = same_ab ? tb : ctx->pat_ta.as<unsigned char>();
+    unsigned char *ta = same_ab ? tb : slice ? tb + ctx->slice_e0 : ctx->pat_ta.as<unsigned char>();
     int *rcnt = ctx->rc.as<int>();
     Counters *d_ctr = ctx->counters.as<Counters>();
     const long long spanA = (long long)plan.DA.back() - plan.DA.front() + 1, spanB = (long long)plan.DB.back() - plan.DB.front() + 1;
     // A first (when it is not B itself): its column range tells which rows of B this product reads -- in a
     // multi-GPU row block that is a fraction of B, and only those rows are coded and checked
-    if (!same_ab)
+    if (slice)
+        CU(cudaMemcpyAsync(d_ctr->a_col_range, ctx->slice_range.p, 2 * sizeof(int), cudaMemcpyDeviceToDevice, s), "row range of the block");
+    else if (!same_ab)
         CU(launch_pat_codes(lc, ctx->m, ctx->k, ctx->A.rowptr, ctx->A.col, t.offsA, t.nDA, spanA, ta, nullptr, &d_ctr->bad_A,
                             &d_ctr->pat_miss, 0ull, nullptr, d_ctr->a_col_range, nullptr),
            "pattern codes of A");
@@ -487,7 +493,7 @@ int bhb200_free_mem(bhb200_ctx *ctx)
                       &ctx->cdf_colcount, &ctx->cdf_hist, &ctx->cdf_tab, &ctx->ct_off, &ctx->ct_col, &ctx->ct_val, &ctx->retry_q,
                       &ctx->brange, &ctx->rlo, &ctx->rspan, &ctx->wl_off, &ctx->wl_cnt, &ctx->wl_idx, &ctx->wl_bits,
                       &ctx->prod, &ctx->rc, &ctx->queue, &ctx->rowoff64, &ctx->rowptr32, &ctx->blocksums,
-                      &ctx->counters, &ctx->bitmap, &ctx->prefix, &ctx->colC, &ctx->valC};
+                      &ctx->counters, &ctx->bitmap, &ctx->prefix, &ctx->colC, &ctx->valC, &ctx->slice_range};
     for (DevBuf *b : bufs) b->release(&ctx->dev_bytes);
     ctx->bitmap_zeroed_bytes = 0;
     cudaGetLastError();

@@ -89,6 +89,10 @@ struct bhb200_ctx {
     bool have_data = false;
     bool borrowed = false;
     bool aliased = false;   // host API: A and B were the same host arrays, uploaded once
+    // multi-GPU row block: A's entries ARE entries slice_e0 .. of B's arrays (bhb200_dist_setup_square), -1 otherwise;
+    // slice_range = {max, INT_MAX - min} over A's columns and A's own rows: the rows of B whose codes the product needs
+    long long slice_e0 = -1;
+    bhb::DevBuf slice_range;
     int dtype = BHB200_DTYPE_F64;
     int m = 0, k = 0, n = 0, nnzA = 0, nnzB = 0;
     bhb::DevBuf a_rowptr, a_col, a_val, b_rowptr, b_col, b_val;

@@ -14,6 +14,7 @@
 //     turns the local row pointers into global ones -- no host round trip per step.
 // NCCL is opened with dlopen at the first bhb200_dist_* call: the single-GPU library has no link
 // dependency on it.
+#include <algorithm>
 #include "context.h"
 
 #include <dlfcn.h>
@@ -168,6 +169,24 @@ __global__ void k_rebase_rowptr(const int rows, const int *__restrict__ rowptr, 
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= rows) out[i] = rowptr[first + i] - rowptr[first];
+}
+
+// {max, INT_MAX - min} over the columns of a block of A and the block's own rows [r0, r1): the rows of B a
+// diagonal-pattern product has to code when A's entries are a slice of B's (context.cu::run_pattern)
+__global__ void k_slice_range(const long long nnz, const int *__restrict__ col, const int r0, const int r1, int *__restrict__ out)
+{
+    int mx = r1 - 1, mn = r0;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
+        const int c = col[j];
+        mx = max(mx, c);
+        mn = min(mn, c);
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&out[0], mx);
+        atomicMax(&out[1], 0x7fffffff - mn);
+    }
 }
 
 __global__ void k_put_count(const Counters *__restrict__ ctr, long long *__restrict__ slot)
@@ -365,6 +384,15 @@ int bhb200_dist_setup_square(bhb200_ctx *ctx, int root, int dtype, int n, int64_
         k_rebase_rowptr<<<(rows + 256) / 256, 256, 0, s>>>(rows, b_rowptr, (int)r0, ctx->a_rowptr.as<int>());
         DCU(cudaGetLastError(), "rebase kernel");
         ctx->A = Csr{ctx->a_rowptr.as<int>(), b_col + e0, (const char *)b_val + (size_t)e0 * vs};
+    }
+    ctx->slice_e0 = -1;
+    if (d->nranks > 1 && rows > 0 && ctx->slice_range.reserve(2 * sizeof(int), &ctx->dev_bytes) == cudaSuccess) {
+        DCU(cudaMemsetAsync(ctx->slice_range.p, 0, 2 * sizeof(int), s), "memset");
+        const long long na = e1 - e0;
+        const int blocks = (int)std::min<long long>((na + 255) / 256 + 1, 1184);
+        k_slice_range<<<blocks, 256, 0, s>>>(na, b_col + e0, (int)r0, (int)r1, ctx->slice_range.as<int>());
+        DCU(cudaGetLastError(), "slice range kernel");
+        ctx->slice_e0 = e0;
     }
     ctx->dtype = dtype;
     ctx->m = rows;

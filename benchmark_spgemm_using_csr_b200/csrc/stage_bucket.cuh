@@ -249,11 +249,9 @@ __device__ __forceinline__ int b3_sort_emit(VT *v, int *c, unsigned *meta, int *
             if (!big) {
                 // (a fixed, predicated trip count of 6 with the longer buckets on the warp path was measured
                 // slower than this loop: too many members took the warp path)
+                // (ci, i) < (cc, mine)  <=>  ci < cc + (i < mine): members before mine count when they are <= cc
                 int r = s;
-                for (int i = s; i < e; ++i) {
-                    const int ci = key2[i];
-                    r += (ci < cc || (ci == cc && i < mine)) ? 1 : 0;
-                }
+                for (int i = s; i < e; ++i) r += (key2[i] < cc + (i < mine ? 1 : 0)) ? 1 : 0;
                 c[r] = cc;
                 perm[r] = (unsigned short)t;
             }

@@ -1,9 +1,7 @@
-export BHB200_PATTERN=off
-( timeout 600 python -m pytest tests/test_spgemm_gpu.py -x -q -m gpu -k "bucket or wide or heavy or rmat or spill" ) > gpurun_out/b3_pytest.log 2>&1
-tail -3 gpurun_out/b3_pytest.log
-( BHB200_DEBUG_FORCE_HEAVY=1 timeout 300 python tools/bucket_dev.py check 17 19 ) > gpurun_out/b3_check.log 2>&1
-grep -c OK gpurun_out/b3_check.log; grep FAIL gpurun_out/b3_check.log
-( BHB200_DEBUG_FORCE_HEAVY=1 timeout 200 python tools/bucket_dev.py bins 21 ) > gpurun_out/b3_bins_v3e_heavy2.txt 2>&1
-( timeout 300 python tools/block_report.py 8 0 ) > gpurun_out/b3_block_s24_r0_e.txt 2>&1
-( timeout 300 python tools/block_report.py 8 3 ) > gpurun_out/b3_block_s24_r3_e.txt 2>&1
-for f in gpurun_out/b3_bins_v3e*.txt gpurun_out/b3_block_s24_r*_e.txt; do echo $f; grep -B1 -A3 "^total" $f | cut -c1-900; done
+( timeout 900 python -m pytest tests -x -q -m gpu --durations=5 ) > gpurun_out/gputest_r02_s2.log 2>&1
+tail -8 gpurun_out/gputest_r02_s2.log
+( timeout 600 python bench.py ) > gpurun_out/bench_r02_s2_n1.json 2> gpurun_out/bench_r02_s2_n1.err
+tail -c 1500 gpurun_out/bench_r02_s2_n1.json; tail -3 gpurun_out/bench_r02_s2_n1.err
+( timeout 300 python bench.py --impl reference ) > gpurun_out/bench_r02_s2_n1_ref.json 2> gpurun_out/bench_r02_s2_n1_ref.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02_s2.csv python bench.py --steps 2 --warmup 1 --no-rmat > gpurun_out/ncu_l2.log 2>&1
+tail -2 gpurun_out/ncu_l2.log | cut -c1-300
