@@ -592,6 +592,12 @@ cudaError_t launch_num_bucket_heavy_f32(const LaunchCtx &lc, const int *queue, i
                                         const unsigned *cdf, int cdf_shift, unsigned long long *cursor);
 cudaError_t launch_num_bucket_heavy_f64(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
                                         const unsigned *cdf, int cdf_shift, unsigned long long *cursor);
+// warp-per-row bucket sort (k_num_bucket3w): bins SB_G128 (capw 128) / SB_G256 (capw 256) whose rows barely compress;
+// sg = lanes per B row (8 | 32); rows staged `stride` apart, rows with more outputs go to d.retry_queue
+cudaError_t launch_num_bucket3w_f32(const LaunchCtx &lc, int capw, int sg, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                    const unsigned *cdf, int cdf_shift, int stride);
+cudaError_t launch_num_bucket3w_f64(const LaunchCtx &lc, int capw, int sg, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                    const unsigned *cdf, int cdf_shift, int stride);
 // second formulation (k_num_bucket_heavy2): rows with more than d.p_lo products, partitioned by slice through their own
 // staging area; rows it cannot slice go to d.retry_queue / d.retry_cnt for launch_num_bucket_heavy_* (d.count_dev)
 cudaError_t launch_num_bucket_heavy2_f32(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
@@ -602,7 +608,7 @@ cudaError_t launch_num_bucket_heavy2_f64(const LaunchCtx &lc, const int *queue, 
 cudaError_t launch_build_cdf(const LaunchCtx &lc, int m, int k, int n, int nnzA, Csr A, Csr B, int *colcountA,
                              unsigned long long *hist, unsigned *cdf, int *shift_out);
 cudaError_t launch_copy_ct(const LaunchCtx &lc, int dtype, const int *queue, int count, const int64_t *rowoff,
-                           const long long *ct_off, const int *ctcol, const void *ctval, int *colC, void *valC);
+                           const long long *ct_off, const int *ctcol, const void *ctval, int *colC, void *valC, double avg_row);
 cudaError_t launch_num_large_f32(const LaunchCtx &lc, const int *queue, int count, int n, Csr A, Csr B,
                                  const int64_t *rowoff, int *colC, float *valC, unsigned *bitmap_scratch,
                                  int *prefix_scratch, int scratch_blocks);

@@ -702,6 +702,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     int spec_cap[MAX_BINS] = {0};
     bool spec_wide[MAX_BINS] = {false};
     bool spec_heavy[MAX_BINS] = {false};   // rows beyond the on-chip tables: sliced bucket sort (k_num_bucket_heavy)
+    bool spec_3w[MAX_BINS] = {false};      // SB_G128 / SB_G256 whose rows barely compress: warp-per-row bucket sort (k_num_bucket3w)
     long long heavy_base = 0;
     long long spec_base[MAX_BINS] = {0};
     long long ct_entries = 0;
@@ -738,6 +739,12 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                     const int nsample = (hc.sym_bin[b] + SAMPLE_STRIDE - 1) / SAMPLE_STRIDE;
                     const double mean = (double)ctx->h_ctr->sample_sum[b] / nsample;
                     const int wcap = WIDE_CAP[b - SB_G128];
+                    // bins of at most 96 / 192 products whose sampled rows keep at least half of their products as outputs:
+                    // sorting the products (k_num_bucket3w) beats hashing them (BHB200_BUCKET_W=off: hash kernels)
+                    static const bool w_on = [] { const char *e = getenv("BHB200_BUCKET_W"); return !(e && strcmp(e, "off") == 0); }();
+                    if (w_on && ctx->bucket_enable && b <= SB_G256 && !force && hc.sym_bin[b] > 0 &&
+                        mean * 2.0 * (double)hc.sym_bin[b] >= (double)hc.sym_bin_products[b])
+                        spec_3w[b] = true;
                     if (smax <= 128) {
                         spec_cap[b] = smax <= 32 ? 32 : smax <= 64 ? 64 : 128;
                     } else if (ctx->direct_wide && !force && mean * 4.0 >= wcap) {
@@ -820,6 +827,7 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     bool use_bucket = false;
     int cdf_shift = 0;
     if (ctx->bucket_enable && spec_mask) {
+        for (int b = SB_G128; b <= SB_G256; ++b) use_bucket |= ((spec_mask >> b) & 1u) && spec_3w[b];
         for (int b = SB_G512; b <= SB_B8192; ++b) use_bucket |= ((spec_mask >> b) & 1u) && spec_wide[b] && spec_cap[b] >= ctx->bucket_min_cap;
         for (int b = SB_B16384; b <= SB_LARGE; ++b) use_bucket |= ((spec_mask >> b) & 1u) && spec_heavy[b];
         if (use_bucket && (ctx->cdf_colcount.reserve(((size_t)ctx->k + 1) * 4, &ctx->dev_bytes) != cudaSuccess ||
@@ -890,6 +898,21 @@ int bhb200_spgemm(bhb200_ctx *ctx)
         if ((spec_mask >> b) & 1u) {
             DirectOut d{rcnt, ctx->ct_off.as<long long>(), ctx->ct_col.as<int>(), ctx->ct_val.p, spec_base[b],
                         ctx->retry_q.as<int>() + so.off[b], &d_ctr->retry_cnt[b]};
+            if (spec_3w[b] && use_bucket) {
+                const int capw = b == SB_G128 ? 128 : 256;
+                if (ctx->dtype == BHB200_DTYPE_F64)
+                    CU(launch_num_bucket3w_f64(lc, capw, G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, spec_cap[b]),
+                       "warp bucket numeric f64");
+                else
+                    CU(launch_num_bucket3w_f32(lc, capw, G, queue + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, d, ctx->cdf_tab.as<unsigned>(), cdf_shift, spec_cap[b]),
+                       "warp bucket numeric f32");
+                if (!spec_wide[b])
+                    CU(launch_sym_hash(lc, b, G, ctx->retry_q.as<int>() + so.off[b], hc.sym_bin[b], ctx->A, ctx->B, rcnt, 1,
+                                       nullptr, &d_ctr->retry_cnt[b]),
+                       "symbolic retry");
+                st.direct_rows += hc.sym_bin[b];
+                continue;
+            }
             // wide bins: the rows up to half the capacity run with the half-size table
             const int passes = spec_wide[b] ? 2 : 1;
             for (int pass = 0; pass < passes; ++pass) {
@@ -992,7 +1015,8 @@ int bhb200_spgemm(bhb200_ctx *ctx)
     if (hc.num_bin[NB_COPY] > 0) {
         CU(stamp(ctx, 1, NB_COPY), "event");
         CU(launch_copy_ct(lc, ctx->dtype, queue + no.off[NB_COPY], hc.num_bin[NB_COPY], rowoff, ctx->ct_off.as<long long>(),
-                          ctx->ct_col.as<int>(), ctx->ct_val.p, colC, valC),
+                          ctx->ct_col.as<int>(), ctx->ct_val.p, colC, valC,
+                          (double)hc.num_bin_nnzc[NB_COPY] / (double)hc.num_bin[NB_COPY]),
            "Ct -> C copy");
     }
     CU(stamp(ctx, 1, MAX_BINS), "event");

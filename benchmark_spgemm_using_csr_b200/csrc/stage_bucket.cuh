@@ -446,6 +446,212 @@ k_num_bucket3(const int *__restrict__ queue, const int count, const int *__restr
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_num_bucket3w: the same single-pass bucket sort with ONE WARP PER ROW, for the bins of at most 96 / 192 products
+// (SB_G128, SB_G256) when their rows barely compress (uniform random operands: BASELINE config 4, 8 x 8 = 64
+// products -> 64 outputs per row; the small rows of R-MAT).  The hash kernel spends ~700 warp instructions per
+// 64-product row, most of them in the register bitonic network and the table re-lookup of the emit.
+//   * SG lanes per B row (8 when the B rows are short: four B rows per warp step, all lanes busy for 8-entry rows);
+//   * the row's A entries are read 32 at a time, their first product indices come from a warp scan;
+//   * bucket / arrival / rank / emit as in k_num_bucket3, at warp scope (__syncwarp only), one emit sweep;
+//   * tight direct bins (DirectOut: rows staged `stride` entries apart, stride < product bound): entries beyond the
+//     stride are not written and the row goes to the retry queue, like k_num_direct.
+// Shared memory per warp: CAPW * (sizeof(VT) + 4 + 4 + 2 + 1) + (CAPW/2 + 1) * 4; the 1024-knot CDF once per CTA.
+// ---------------------------------------------------------------------------------------------------
+constexpr int B3W_KB = 10;
+constexpr int B3W_WARPS = 8;
+
+template <typename VT, int CAPW>
+__host__ __device__ constexpr size_t b3w_per_warp()
+{
+    return (((size_t)CAPW * (sizeof(VT) + 4 + 4 + 2 + 1) + (size_t)(CAPW / 2 + 1) * 4) + 15) & ~(size_t)15;
+}
+
+template <typename VT, int CAPW, int SG>
+__global__ void __launch_bounds__(B3W_WARPS * 32, 6)
+k_num_bucket3w(const int *__restrict__ queue, const int count, const int *__restrict__ rowptrA, const int *__restrict__ colA,
+               const VT *__restrict__ valA, const int *__restrict__ rowptrB, const int *__restrict__ colB,
+               const VT *__restrict__ valB, const ColumnCdf cdf, int *__restrict__ rc, long long *__restrict__ ct_off,
+               int *__restrict__ ctcol, VT *__restrict__ ctval, const long long ct_base, const int stride,
+               int *__restrict__ retry_queue, int *__restrict__ retry_cnt)
+{
+    constexpr int K = 1 << B3W_KB;
+    constexpr int NB = CAPW / 2;
+    constexpr int PER = (NB + 1 + 31) / 32;   // counters per lane in the warp scan
+    static_assert(CAPW <= 256 && NB <= 256, "bucket and arrival are one byte each");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned *scdf = reinterpret_cast<unsigned *>(smem_raw);   // [K + 1] (+ padding to 16 bytes)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned char *mine = smem_raw + (((size_t)(K + 1) * 4 + 15) & ~(size_t)15) + (size_t)w * b3w_per_warp<VT, CAPW>();
+    VT *v = reinterpret_cast<VT *>(mine);                                   // [CAPW]
+    int *c = reinterpret_cast<int *>(v + CAPW);                             // [CAPW] staged columns, later the sorted ones
+    int *key2 = c + CAPW;                                                   // [CAPW]
+    int *cnt = key2 + CAPW;                                                 // [NB + 1]
+    unsigned short *meta = reinterpret_cast<unsigned short *>(cnt + NB + 1);   // [CAPW] bucket << 8 | arrival
+    unsigned char *perm = reinterpret_cast<unsigned char *>(meta + CAPW);   // [CAPW]
+
+    constexpr int DEC = CDF_BITS - B3W_KB;
+    for (int i = threadIdx.x; i <= K; i += B3W_WARPS * 32) scdf[i] = cdf.cdf[i << DEC];
+    __syncthreads();
+    const int sh = cdf.shift + DEC;
+    const unsigned fmask = (1u << sh) - 1u;
+
+    // (Measured and dropped: issuing the queue -> rowptrA -> colA -> rowptrB chain of the NEXT row before the current row
+    // is processed -- 8 more registers, one CTA less per SM: config 4 3.58 -> 3.87 ms.)
+    for (int q = blockIdx.x * B3W_WARPS + w; q < count; q += gridDim.x * B3W_WARPS) {   // warp-uniform, no CTA barrier inside
+        const int row = queue[q];
+        for (int i = lane; i <= NB; i += 32) cnt[i] = 0;
+        __syncwarp();
+        const int a0 = rowptrA[row], a1 = rowptrA[row + 1];
+        int p = 0;   // products staged so far (warp-uniform)
+        for (int jr = a0; jr < a1; jr += 32) {
+            const int j = jr + lane;
+            int bs = 0, len = 0;
+            VT av = VT(0);
+            if (j < a1) {
+                const int k = colA[j];
+                bs = rowptrB[k];
+                len = rowptrB[k + 1] - bs;
+                av = valA[j];
+            }
+            int incl = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += y;
+            }
+            const int tb = p + incl - len;
+            p += __shfl_sync(FULL, incl, 31);
+            const int nent = min(32, a1 - jr);
+            constexpr int EPP = 32 / SG;   // A entries per warp step
+            for (int e0 = 0; e0 < nent; e0 += EPP) {
+                const int src = e0 + lane / SG;   // (entries past the row's end carry length 0)
+                const int s_bs = __shfl_sync(FULL, bs, src & 31), s_len = (src < 32) ? __shfl_sync(FULL, len, src & 31) : 0;
+                const int s_tb = __shfl_sync(FULL, tb, src & 31);
+                const VT s_av = __shfl_sync(FULL, av, src & 31);
+                const int max_len = (SG == 32) ? s_len : __reduce_max_sync(FULL, s_len);
+                for (int off0 = 0; off0 < max_len; off0 += SG) {
+                    const int off = off0 + (lane & (SG - 1));
+                    if (off < s_len && s_tb + off < CAPW) {
+                        const int cc = colB[s_bs + off];
+                        const VT vv = s_av * valB[s_bs + off];
+                        const int i = cc >> sh;
+                        const unsigned lo = scdf[i], hi = scdf[i + 1];
+                        const unsigned f = lo + (unsigned)(((unsigned long long)(hi - lo) * ((unsigned)cc & fmask)) >> sh);
+                        const unsigned b = __umulhi(f, (unsigned)NB);
+                        const unsigned arr = (unsigned)atomicAdd(&cnt[b], 1);
+                        const int t = s_tb + off;
+                        c[t] = cc;
+                        v[t] = vv;
+                        meta[t] = (unsigned short)((b << 8) | arr);
+                    }
+                }
+            }
+        }
+        p = min(p, CAPW);   // (the bin's product bound is below CAPW; the guard above keeps a wrong bin from writing out of bounds)
+        __syncwarp();
+        // ---- warp scan of the counters: cnt[b] = first slot of bucket b, cnt[NB] = p ----
+        {
+            int run = 0;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int i = lane * PER + u;
+                if (i <= NB) {
+                    const int x = cnt[i];
+                    cnt[i] = run;
+                    run += x;
+                }
+            }
+            int incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += y;
+            }
+            const int before = incl - run;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int i = lane * PER + u;
+                if (i <= NB) cnt[i] += before;
+            }
+        }
+        __syncwarp();
+        for (int t = lane; t < p; t += 32) {
+            const unsigned m = meta[t];
+            key2[cnt[m >> 8] + (int)(m & 0xffu)] = c[t];
+        }
+        __syncwarp();
+        for (int t0 = 0; t0 < p; t0 += 32) {
+            const int t = t0 + lane;
+            int s = 0, e = 0, mine_slot = 0, cc = 0;
+            bool big = false;
+            if (t < p) {
+                const unsigned m = meta[t];
+                const int b = (int)(m >> 8);
+                s = cnt[b];
+                e = cnt[b + 1];
+                mine_slot = s + (int)(m & 0xffu);
+                cc = key2[mine_slot];
+                big = e - s > B3_BIG;
+                if (!big) {
+                    int r = s;
+                    for (int i = s; i < e; ++i) r += (key2[i] < cc + (i < mine_slot ? 1 : 0)) ? 1 : 0;
+                    c[r] = cc;
+                    perm[r] = (unsigned char)t;
+                }
+            }
+            unsigned bm = __ballot_sync(FULL, big);
+            while (bm) {
+                const int src = __ffs(bm) - 1;
+                bm &= bm - 1;
+                const int ss = __shfl_sync(FULL, s, src), ee = __shfl_sync(FULL, e, src);
+                const int mm = __shfl_sync(FULL, mine_slot, src), xc = __shfl_sync(FULL, cc, src);
+                int part = 0;
+                for (int i = ss + lane; i < ee; i += 32) part += (key2[i] < xc + (i < mm ? 1 : 0)) ? 1 : 0;
+                part = __reduce_add_sync(FULL, part);
+                if (lane == src) {
+                    c[ss + part] = cc;
+                    perm[ss + part] = (unsigned char)t;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- emit (one sweep: the warp walks the sorted row front to back) ----
+        const long long o = ct_base + (long long)q * stride;
+        int base = 0;
+        for (int rb = 0; rb < p; rb += 32) {
+            const int r = rb + lane;
+            int cc = -1;
+            bool head = false;
+            if (r < p) {
+                cc = c[r];
+                head = r == 0 || cc != c[r - 1];
+            }
+            const unsigned bal = __ballot_sync(FULL, head);
+            if (head) {
+                VT sum = v[perm[r]];
+                for (int rr = r + 1; rr < p && c[rr] == cc; ++rr) sum += v[perm[rr]];
+                const int at = base + __popc(bal & ((1u << lane) - 1u));
+                if (at < stride) {
+                    ctcol[o + at] = cc;
+                    ctval[o + at] = sum;
+                }
+            }
+            base += __popc(bal);
+        }
+        if (lane == 0) {
+            if (base > stride && retry_queue) {   // tight bin: more outputs than the speculated capacity -> two-pass path
+                ct_off[row] = -1;
+                retry_queue[atomicAdd(retry_cnt, 1)] = row;
+            } else {
+                ct_off[row] = o;
+                rc[row] = base;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_num_bucket_heavy: the same bucket sort for rows with MORE products than fit on chip (the rows the
 // reference sends through EM_mergepath_global, bhsparse_cuda.h:2270-2525, and round 1 sent through a global
 // column bitmap -- at n = 16.8 M columns, config 5, that kernel ran at 6 products/ns and held rank 0 at 99 ms

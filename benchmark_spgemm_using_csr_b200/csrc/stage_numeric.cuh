@@ -861,6 +861,41 @@ static cudaError_t launch_num_bucket_t(const LaunchCtx &lc, int cap, const int *
     return launch_num_bucket_tt<VT, 1024>(lc, cap, queue, count, A, B, d, cdf);
 }
 
+// warp-per-row bucket sort for the bins of at most 96 (capw 128) / 192 (capw 256) products; rows staged `stride` apart
+template <typename VT, int CAPW, int SG>
+static cudaError_t launch_num_bucket3w_tt(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d, ColumnCdf cdf,
+                                          int stride)
+{
+    const size_t smem = ((((size_t)(1 << B3W_KB) + 1) * 4 + 15) & ~(size_t)15) + (size_t)B3W_WARPS * b3w_per_warp<VT, CAPW>();
+    auto kern = k_num_bucket3w<VT, CAPW, SG>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    long long blocks = ((long long)count + B3W_WARPS - 1) / B3W_WARPS;
+    const long long lim = (long long)lc.sm_count * resident_blocks(kern, B3W_WARPS * 32, smem);
+    if (blocks > lim) blocks = lim;
+    ++*lc.launches;
+    kern<<<(int)blocks, B3W_WARPS * 32, smem, lc.stream>>>(queue, count, A.rowptr, A.col, (const VT *)A.val, B.rowptr, B.col,
+                                                          (const VT *)B.val, cdf, d.rc, d.ct_off, d.ctcol, (VT *)d.ctval, d.ct_base,
+                                                          stride, d.retry_queue, d.retry_cnt);
+    return cudaGetLastError();
+}
+
+template <typename VT>
+static cudaError_t launch_num_bucket3w_t(const LaunchCtx &lc, int capw, int sg, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                         ColumnCdf cdf, int stride)
+{
+    if (count <= 0) return cudaSuccess;
+    if (capw == 128)
+        return sg == 8 ? launch_num_bucket3w_tt<VT, 128, 8>(lc, queue, count, A, B, d, cdf, stride)
+                       : launch_num_bucket3w_tt<VT, 128, 32>(lc, queue, count, A, B, d, cdf, stride);
+    if (capw == 256)
+        return sg == 8 ? launch_num_bucket3w_tt<VT, 256, 8>(lc, queue, count, A, B, d, cdf, stride)
+                       : launch_num_bucket3w_tt<VT, 256, 32>(lc, queue, count, A, B, d, cdf, stride);
+    return cudaErrorInvalidValue;
+}
+
 template <typename VT>
 static cudaError_t launch_num_bucket_heavy_t(const LaunchCtx &lc, const int *queue, int count, Csr A, Csr B, DirectOut d,
                                              ColumnCdf cdf, unsigned long long *cursor)
@@ -914,6 +949,8 @@ static cudaError_t launch_copy_ct_t(const LaunchCtx &lc, const int *queue, int c
     if (count <= 0) return cudaSuccess;
     const int threads = 256;
     ++*lc.launches;
+    // (measured and dropped: a warp per 32 short rows, their {offset, length, staging offset} read with coalesced loads:
+    // config 4's copy 1.50 -> 1.52 ms)
     if (avg_row <= 12.0) {
         const long long blocks = ((long long)count * 8 + threads - 1) / threads;
         k_copy_ct<VT, 8><<<(int)blocks, threads, 0, lc.stream>>>(queue, count, rowoff, ct_off, ctcol, ctval, colC, valC);

@@ -50,4 +50,10 @@ cudaError_t launch_num_bucket_heavy2_f32(const LaunchCtx &lc, const int *queue, 
     return launch_num_bucket_heavy2_t<float>(lc, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift}, cursor);
 }
 
+cudaError_t launch_num_bucket3w_f32(const LaunchCtx &lc, int capw, int sg, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                     const unsigned *cdf, int cdf_shift, int stride)
+{
+    return launch_num_bucket3w_t<float>(lc, capw, sg, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift}, stride);
+}
+
 }  // namespace bhb

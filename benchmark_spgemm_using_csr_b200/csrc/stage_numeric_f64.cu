@@ -33,14 +33,13 @@ cudaError_t launch_num_direct_f64(const LaunchCtx &lc, int cap, int G, const int
 }
 
 cudaError_t launch_copy_ct(const LaunchCtx &lc, int dtype, const int *queue, int count, const int64_t *rowoff,
-                           const long long *ct_off, const int *ctcol, const void *ctval, int *colC, void *valC)
+                           const long long *ct_off, const int *ctcol, const void *ctval, int *colC, void *valC, double avg_row)
 {
-    // rows per launch are not known here: pick the lane width from the bin's average row on the host side later if
-    // it matters; 32 lanes per row suit the >= 32-output rows the direct mode targets
+    // avg_row = staged entries per row of the launch: short rows are copied 32 rows per warp
     return dtype ? launch_copy_ct_t<double>(lc, queue, count, rowoff, ct_off, ctcol, (const double *)ctval, colC,
-                                            (double *)valC, 64.0)
+                                            (double *)valC, avg_row)
                  : launch_copy_ct_t<float>(lc, queue, count, rowoff, ct_off, ctcol, (const float *)ctval, colC,
-                                           (float *)valC, 64.0);
+                                           (float *)valC, avg_row);
 }
 
 cudaError_t launch_num_bucket_f64(const LaunchCtx &lc, int cap, const int *queue, int count, Csr A, Csr B, DirectOut d,
@@ -59,6 +58,12 @@ cudaError_t launch_num_bucket_heavy2_f64(const LaunchCtx &lc, const int *queue, 
                                          const unsigned *cdf, int cdf_shift, unsigned long long *cursor)
 {
     return launch_num_bucket_heavy2_t<double>(lc, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift}, cursor);
+}
+
+cudaError_t launch_num_bucket3w_f64(const LaunchCtx &lc, int capw, int sg, const int *queue, int count, Csr A, Csr B, DirectOut d,
+                                     const unsigned *cdf, int cdf_shift, int stride)
+{
+    return launch_num_bucket3w_t<double>(lc, capw, sg, queue, count, A, B, d, ColumnCdf{cdf, cdf_shift}, stride);
 }
 
 }  // namespace bhb

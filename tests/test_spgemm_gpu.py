@@ -283,6 +283,34 @@ def test_wide_rows_bucket_sort_edges(dt, monkeypatch):
     _check(A, B, f"bucket v1 hub column {dt.__name__}")
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_small_rows_warp_bucket_sort(dt, monkeypatch):
+    """k_num_bucket3w (csrc/stage_bucket.cuh): bins of at most 96 / 192 products whose rows barely compress --
+    BASELINE config 4 in small (8 x 8 products per row, 8 lanes per B row), longer B rows (32 lanes per B row),
+    a tight bin with a few rows beyond the speculated capacity (retry queue), and the hash kernels as a cross-check."""
+    if os.environ.get("BHB200_PATTERN") != "off":
+        pytest.skip("general path only")
+    A = gen.uniform_rect(16384, 4096, 8, seed=1, dtype=dt)
+    B = gen.uniform_rect(4096, 300000, 8, seed=2, value_seed=3, dtype=dt)
+    st = _check(A, B, f"warp bucket 8x8 {dt.__name__}")
+    assert st["direct_rows"] == 16384 and st["direct_retry_rows"] == 0
+    # B rows of 20 entries: 4 x 20 = 80 products (SB_G128) and 8 x 20 = 160 (SB_G256), 32 lanes per B row
+    per_row = np.array([4, 8])[np.arange(2 * 5000) % 2]
+    A2 = gen.random_csr(2 * 5000, 6000, per_row, seed=61, dtype=dt)
+    B2 = gen.random_csr(6000, 2_000_000, 20, seed=62, value_seed=63, dtype=dt)
+    st = _check(A2, B2, f"warp bucket 20-entry B rows {dt.__name__}")
+    assert st["direct_rows"] == 2 * 5000
+    # tight bin: most rows 8 x 8 = 64 outputs, one row in 300 has 11 x 8 = 88 (same bin, beyond a capacity of 64
+    # unless the sample happened to see one)
+    per_row = np.where(np.arange(12000) % 300 == 7, 11, 8)
+    A3 = gen.random_csr(12000, 4096, per_row, seed=64, dtype=dt)
+    st = _check(A3, B, f"warp bucket tight overflow {dt.__name__}")
+    assert st["direct_rows"] == 12000
+    monkeypatch.setenv("BHB200_BUCKET_W", "off")
+    st = _check(A, B, f"hash kernels 8x8 {dt.__name__}")
+    assert st["direct_rows"] == 16384
+
+
 def test_direct_mode_off_matches(monkeypatch):
     if os.environ.get("BHB200_PATTERN") != "off":
         pytest.skip("asserts on the general path's kernels; the pattern mode has its own tests")
