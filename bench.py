@@ -694,6 +694,9 @@ def main():
         "roofline": roofline, "roofline_step": roof_step, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
         "gpu_launches": t["launches"], "clocks": t["clocks"], "nnzC_rank0": t["nnz_local"],
         "rank_ms": {"max": ms, "min": t["ms_min_rank"]},
+        # each rank's own pipeline (its CUDA events inside the library, last step): a step ends in an all-gather, so the
+        # step time follows the slowest rank
+        "pipeline_ms": {"max_rank": t["pipeline_ms_max_rank"], "min_rank": t["pipeline_ms_min_rank"]},
         "stages_ms": {"count_bin": st["ms_count"], "symbolic": st["ms_symbolic"], "scan_alloc": st["ms_scan"],
                       "numeric": st["ms_numeric"], "total": st["ms_total"]},
         "bins_ms": {"symbolic": {SYM_BIN_NAMES[i]: round(float(bin_ms_sym[i]), 4) for i in range(len(SYM_BIN_NAMES)) if bin_ms_sym[i] > 0},
