@@ -872,6 +872,7 @@ k_num_bucket_heavy(const int *__restrict__ queue, const int count, const int *__
 // Rows whose slices still overflow (one column carrying more products than the chip holds, ...) are handed to
 // k_num_bucket_heavy through a retry queue before anything is written or allocated for them.
 // Rows of at most p_lo products are skipped (they are taken by k_num_bucket3 in the same staging area).
+// (Measured and dropped: two B rows per warp step in the count and scatter passes, as in k_num_bucket3 -- no change.)
 // ---------------------------------------------------------------------------------------------------
 constexpr int H2_MAX_LG = 11;   // at most 2048 slices per row (16.7 M products); longer rows -> retry queue
 
