@@ -187,7 +187,10 @@ def config_dict(desc, m, nnzA, products, nnzC, world):
     return {"workload": desc, "values": VALUES, "m": int(m), "nnzA": int(nnzA), "products": int(products),
             "nnzC": int(nnzC), "l2": "inputs larger than L2 (no flush needed)",
             "partition": f"{world} row block(s) on the prefix sum of per-row products",
-            "allocations": "device buffers are grow-only and cached: none inside the timed step after warm-up"}
+            "allocations": "device buffers are grow-only and cached: none inside the timed step after warm-up",
+            "reuse": "per call everything is recomputed from the operands except two hints kept from the previous call on the "
+                     "same operands: the diagonal-offset plan (every entry re-verified against it) and the column CDF that "
+                     "balances the sort buckets (any table gives the same C)"}
 
 
 # =================================================================================================

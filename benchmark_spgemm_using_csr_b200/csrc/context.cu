@@ -60,6 +60,7 @@ void release_operands(bhb200_ctx *ctx)
     ctx->borrowed = false;
     ctx->aliased = false;
     ctx->slice_e0 = -1;
+    ctx->cdf_valid = false;
     ctx->have_C = false;
     ctx->last_pattern = false;
     ctx->nnzC = 0;
@@ -119,6 +120,7 @@ int init_host(bhb200_ctx *ctx, int dtype, int m, int k, int n, int nnzA, const v
     ctx->nnzA = nnzA;
     ctx->nnzB = nnzB;
     ctx->have_data = true;
+    ctx->cdf_valid = false;   // new operands: the column CDF of the previous ones is not reused
     ctx->borrowed = false;
     ctx->have_C = false;
     ctx->nnzC = 0;
@@ -572,6 +574,7 @@ int bhb200_init_data_device(bhb200_ctx *ctx, int dtype, int m, int k, int n, int
     ctx->nnzA = nnzA;
     ctx->nnzB = nnzB;
     ctx->have_data = true;
+    ctx->cdf_valid = false;   // new operands: the column CDF of the previous ones is not reused
     ctx->borrowed = true;
     return BHB200_SUCCESS;
 }
@@ -841,10 +844,16 @@ int bhb200_spgemm(bhb200_ctx *ctx)
                     spec_mask &= ~(1u << b);
                 }
         }
-        if (use_bucket)
+        static const bool cdf_rebuild = [] { const char *e = getenv("BHB200_CDF"); return e && strcmp(e, "rebuild") == 0; }();
+        if (use_bucket && ctx->cdf_valid && !cdf_rebuild) {
+            cdf_shift = ctx->cdf_shift_cached;
+        } else if (use_bucket) {
             CU(launch_build_cdf(lc, ctx->m, ctx->k, ctx->n, ctx->nnzA, ctx->A, ctx->B, ctx->cdf_colcount.as<int>(),
                                 ctx->cdf_hist.as<unsigned long long>(), ctx->cdf_tab.as<unsigned>(), &cdf_shift),
                "column CDF");
+            ctx->cdf_valid = true;
+            ctx->cdf_shift_cached = cdf_shift;
+        }
     }
     // Rows with more products than the on-chip tables hold (bins SB_B16384 .. SB_LARGE), single pass, staged by atomic
     // bump at heavy_base: rows of at most 8192 products by k_num_bucket3 itself, the rest by k_num_bucket_heavy2

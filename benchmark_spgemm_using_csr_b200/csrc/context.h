@@ -102,6 +102,10 @@ struct bhb200_ctx {
     bhb::DevBuf prod, rc, queue, rowoff64, rowptr32, blocksums, counters, bitmap, prefix;
     bhb::DevBuf brange, rlo, rspan, wl_off, wl_cnt, wl_idx, wl_bits;   // span info + word-list pool (range kernels)
     bhb::DevBuf cdf_colcount, cdf_hist, cdf_tab;                          // bucket-sort kernels: column CDF of the products
+    // the table of the previous product on these operands is kept: it only balances the buckets (any monotone table gives
+    // the same C), and it depends on the patterns alone; reset whenever operands are (re)initialised (BHB200_CDF=rebuild: every call)
+    bool cdf_valid = false;
+    int cdf_shift_cached = 0;
     int bucket_min_cap = 512;                                             // smallest wide-bin capacity that takes the bucket kernel (k_num_bucket3 wins from 512 up, r02_notes.md section 5)
     int bucket_heavy = 1;                                                 // BHB200_BUCKET_HEAVY=off: global-bitmap kernels for rows beyond the on-chip tables
     int bucket_enable = 1;                                                // BHB200_BUCKET=off: hash kernels for the wide bins

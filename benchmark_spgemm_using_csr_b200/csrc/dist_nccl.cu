@@ -401,6 +401,7 @@ int bhb200_dist_setup_square(bhb200_ctx *ctx, int root, int dtype, int n, int64_
     ctx->nnzA = (int)(e1 - e0);
     ctx->nnzB = (int)nnz;
     ctx->have_data = true;
+    ctx->cdf_valid = false;   // new operands: the column CDF of the previous ones is not reused
     ctx->borrowed = true;    // (update_values does not apply; the b_* buffers stay library-owned)
     ctx->aliased = false;
     ctx->wait_before_values = d->ev_val;   // the first spgemm waits for the values after its stage 1
