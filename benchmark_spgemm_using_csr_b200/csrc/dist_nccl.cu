@@ -122,17 +122,17 @@ int dfail(bhb200_ctx *c, int code, const char *what, const char *detail = nullpt
         if (r__ != 0) return dfail(ctx, BHB200_ERR_CUDA, what, nccl().GetErrorString ? nccl().GetErrorString(r__) : "NCCL error"); \
     } while (0)
 
-// Cost of a row for the partition: its intermediate products, times 1.25 beyond 12288 products -- rows that
+// Cost of a row for the partition: its intermediate products, times 11/8 beyond 12288 products -- rows that
 // leave the on-chip tables are sliced through global memory (k_num_bucket_heavy2) and cost about that much more per
 // product (R-MAT 24 / 8 blocks: 24.4 products/ns in block 0, which holds the hub rows, 26.1 in block 3;
-// profiles/r02_notes.md section 5.  The factor was 2.5 for the first heavy-row kernel).  dist.py::row_cost is the same function.
+// profiles/r02_notes.md section 5.  The factor was 2.5 for the first heavy-row kernel; with 1.25 block 0 was still the slowest by 3 % at 8 GPUs).  dist.py::row_cost is the same function.
 constexpr int COST_HEAVY_ROW = 12288;
 __global__ void k_row_cost(const int n, const int *__restrict__ prod, int *__restrict__ cost)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long p = prod[i];
-    const long long c = p > COST_HEAVY_ROW ? (p * 5) / 4 : p;
+    const long long c = p > COST_HEAVY_ROW ? (p * 11) / 8 : p;
     cost[i] = (int)(c > 0x7fffffffLL ? 0x7fffffffLL : c);
 }
 

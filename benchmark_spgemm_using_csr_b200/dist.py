@@ -47,12 +47,12 @@ COST_HEAVY_ROW = 12288
 
 def row_cost(row_products: np.ndarray) -> np.ndarray:
     """Cost of a row for the partition (csrc/dist_nccl.cu::k_row_cost is the same function): its
-    intermediate products, times 1.25 beyond 12288 products -- rows that leave the on-chip tables (sliced
+    intermediate products, times 11/8 beyond 12288 products -- rows that leave the on-chip tables (sliced
     through global memory by k_num_bucket_heavy2) cost about that much more per product, and R-MAT's hub rows all
     sit in the first block (R-MAT 24 / 8 blocks, measured per block: 24.4 products/ns in block 0, 26.1 in block 3;
-    the factor was 2.5 for the first heavy-row kernel)."""
+    the factor was 2.5 for the first heavy-row kernel; 1.25 left block 0 the slowest by 3 % at 8 GPUs)."""
     p = row_products.astype(np.int64)
-    return np.minimum(np.where(p > COST_HEAVY_ROW, (p * 5) // 4, p), np.int64(0x7FFFFFFF))
+    return np.minimum(np.where(p > COST_HEAVY_ROW, (p * 11) // 8, p), np.int64(0x7FFFFFFF))
 
 
 def partition_rows_by_products(row_products: np.ndarray, world: int) -> np.ndarray:
@@ -248,7 +248,7 @@ class RowBlockSpGEMM:
             prefix = torch.zeros(n + 1, dtype=torch.int64, device=dev)
             torch.cumsum(prods, 0, out=prefix[1:])
             total = int(prefix[-1].item())
-            cost = torch.where(prods > COST_HEAVY_ROW, (prods * 5) // 4, prods).clamp(max=0x7FFFFFFF)      # row_cost()
+            cost = torch.where(prods > COST_HEAVY_ROW, (prods * 11) // 8, prods).clamp(max=0x7FFFFFFF)      # row_cost()
             cprefix = torch.zeros(n + 1, dtype=torch.int64, device=dev)
             torch.cumsum(cost, 0, out=cprefix[1:])
             ctotal = int(cprefix[-1].item())

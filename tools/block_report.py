@@ -20,7 +20,7 @@ lenB = (rp[1:] - rp[:-1]).to(torch.int64)
 csum = torch.zeros(col.numel() + 1, dtype=torch.int64, device=dev)
 torch.cumsum(lenB[col.to(torch.int64)], 0, out=csum[1:])
 prods = csum[rp[1:].to(torch.int64)] - csum[rp[:-1].to(torch.int64)]
-cost = torch.where(prods > COST_HEAVY_ROW, (prods * 5) // 4, prods)
+cost = torch.where(prods > COST_HEAVY_ROW, (prods * 11) // 8, prods)
 cpre = torch.zeros(n + 1, dtype=torch.int64, device=dev)
 torch.cumsum(cost, 0, out=cpre[1:])
 tot = int(cpre[-1])
