@@ -65,6 +65,21 @@ def test_config4_uniform_rect_f32():
     _full_compare(A, B, "C4", P=268435456)
 
 
+def test_config2_and_config4_real_values_within_tolerance():
+    """one extra run per config with uniform reals -- the tolerance path at full size
+    (BASELINE.json: <= 1e-12 relative in double, <= 1e-5 in float; structure bit-exact)."""
+    A = gen.poisson27pt(128, 128, 128)
+    A = gen.CSR(A.rows, A.cols, A.rowptr, A.col, gen.real_values(A.col.size, 11, np.float64))
+    rp, col, val = spgemm(A, A)
+    assert_csr_equal((rp, col, val), _oracle(A, A), exact_values=False, rtol=1e-12, what="C2 real values")
+    A4 = gen.uniform_rect(4194304, 1048576, per_row=8, seed=1, dtype=np.float32)
+    B4 = gen.uniform_rect(1048576, 4194304, per_row=8, seed=2, value_seed=3, dtype=np.float32)
+    A4 = gen.CSR(A4.rows, A4.cols, A4.rowptr, A4.col, gen.real_values(A4.col.size, 12, np.float32))
+    B4 = gen.CSR(B4.rows, B4.cols, B4.rowptr, B4.col, gen.real_values(B4.col.size, 13, np.float32))
+    rp, col, val = spgemm(A4, B4)
+    assert_csr_equal((rp, col, val), _oracle(A4, B4), exact_values=False, rtol=1e-5, what="C4 real values")
+
+
 @pytest.fixture(scope="module")
 def rmat22():
     return gen.rmat(22, 16)
