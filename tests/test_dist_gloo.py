@@ -105,3 +105,21 @@ def test_partition_properties():
         assert sums.max() <= prods.sum() / world + prods.max()
     assert partition_rows_by_products(np.zeros(10, np.int64), 4).tolist()[-1] == 10
     assert partition_rows_by_products(np.zeros(0, np.int64), 2).tolist() == [0, 0, 0]
+
+
+def test_row_cost_model():
+    """The partition's cost of a row (dist.row_cost == csrc/dist_nccl.cu::k_row_cost): its products, times 11/8 beyond the
+    largest on-chip capacity, clamped to int32 like the device array; blocks are balanced on this cost, never split a row."""
+    from benchmark_spgemm_using_csr_b200.dist import COST_HEAVY_ROW, partition_rows_by_products, row_cost
+    p = np.array([0, 1, 12288, 12289, 16000, 2_000_000_000], dtype=np.int64)
+    c = row_cost(p)
+    assert c.dtype == np.int64 and list(c[:3]) == [0, 1, 12288]
+    assert c[3] == (12289 * 11) // 8 and c[4] == 22000 and c[5] == 0x7FFFFFFF
+    assert np.all(np.diff(row_cost(np.arange(COST_HEAVY_ROW - 4, COST_HEAVY_ROW + 4))) >= 0)      # monotone across the threshold
+    rng = np.random.default_rng(3)
+    prods = rng.integers(0, 40000, size=5000)
+    cost = row_cost(prods)
+    b = partition_rows_by_products(cost, 8)
+    assert b[0] == 0 and b[-1] == prods.size and np.all(np.diff(b) >= 0)
+    share = np.add.reduceat(cost, b[:-1])[:8]
+    assert share.max() - share.min() <= 2 * cost.max()      # equal shares up to one row
